@@ -1,0 +1,103 @@
+"""Pin the CPU oracle against fixtures produced by the REFERENCE's own numpy code
+(tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import oracle as orc
+from smplsim_b200.abi import env_cfg_from
+from smplsim_b200.cfg import make_cfg
+from smplsim_b200.model import load_model
+
+
+def _om(robot="smpl_humanoid", env="speed", **ov):
+    cfg = make_cfg(env=env, robot=robot, overrides={f"env.{k}" if "." not in k else k: v for k, v in ov.items()})
+    return orc.OracleModel.from_cfg(cfg), cfg
+
+
+@pytest.mark.parametrize("name,robot", [("smpl", "smpl_humanoid"), ("smplx", "smplx_humanoid")])
+@pytest.mark.parametrize("upright,rh", [(False, True), (False, False), (True, True)])
+def test_self_obs_v1_v2_match_reference(name, robot, upright, rh):
+    g = np.load(os.path.join(GOLDEN, f"obs_{name}.npz"))
+    om, _ = _om(robot, **{"root_height_obs": rh, "robot.has_upright_start": upright})
+    tag = f"u{int(upright)}h{int(rh)}"
+    for i in range(g["qpos"].shape[0]):
+        o1 = orc.self_obs(om, 1, g["qvel"][i], g["xpos"][i], g["xquat"][i])
+        o2 = orc.self_obs(om, 2, g["qvel"][i], g["xpos"][i], g["xquat"][i], g["linvel"][i], g["angvel"][i])
+        np.testing.assert_allclose(o1, g["v1_" + tag][i], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(o2, g["v2_" + tag][i], rtol=0, atol=1e-12)
+
+
+def test_k7a_default_pose_vector():
+    """reference-generated seed vector at the Default pose."""
+    g = np.load(os.path.join(GOLDEN, "obs_smpl.npz"))
+    v2 = g["v2_u0h1"][0]
+    np.testing.assert_allclose(v2[:7], [0.94, -0.0068, 0.0695, -0.0914, -0.0113, 0.1038, -0.4666], atol=1e-4)
+    assert abs(v2[: 1 + 69 + 144].sum() - 49.6512) < 1e-3
+    np.testing.assert_allclose(v2[70:76], [0, 1, 0, 1, 0, 0], atol=1e-12)
+
+
+def test_task_obs_and_rewards_match_reference():
+    g = np.load(os.path.join(GOLDEN, "obs_smpl.npz"))
+    B = g["qpos"].shape[0]
+    for task, key_obs, key_rew in (("speed", "speed_obs", "speed_rew"), ("reach", "reach_obs", "reach_rew"), ("getup", None, "getup_rew")):
+        om, cfg = _om(env=task)
+        e = orc.OracleEnv(om)
+        for i in range(B):
+            e.qpos[:] = g["qpos"][i]
+            e.qvel[:] = 0
+            if task == "speed":
+                e.target[0] = g["tar_speed"][i]
+            elif task == "reach":
+                e.target[:3] = g["tar_pos"][i]
+            else:
+                e.target[0] = g["tar_h"][i]
+            obs = e.observations()
+            if key_obs:
+                np.testing.assert_allclose(obs[-3:], g[key_obs][i], atol=1e-12)
+            else:
+                assert obs[-1] == g["tar_h"][i]
+            # reward through a zero-length step is not exposed; use the closed forms on oracle xpos
+            if task == "speed":
+                d = (e.xpos[0] - g["prev_root"][i]) * 30.0
+                r = np.exp(-0.25 * ((g["tar_speed"][i] - d[0]) ** 2 + 0.1 * d[1] ** 2))
+            elif task == "reach":
+                r = np.exp(-4 * np.sum((g["tar_pos"][i] - e.xpos[-1]) ** 2))
+            else:
+                r = np.exp(-4 * (g["tar_h"][i] - e.xpos[0, 2]) ** 2)
+            assert abs(r - g[key_rew][i]) < 1e-12
+
+
+def test_gains_and_action_scale_match_reference():
+    g = np.load(os.path.join(GOLDEN, "controllers_smpl.npz"))
+    m = load_model("smpl", control_mode="uhc_pd")
+    np.testing.assert_array_equal(m.act_kp, g["jkp"])
+    np.testing.assert_array_equal(m.act_kd, g["jkd"])
+    np.testing.assert_array_equal(m.act_torque_lim, g["torque_lim"])
+    np.testing.assert_allclose(m.act_scale, g["pd_action_scale"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(m.act_offset, g["pd_action_offset"], rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("mode,key,ps", [("uhc_pd", "torque_spd", 10), ("pd", "torque_pd", 10), ("torque", "torque_torque", 10)])
+def test_controllers_match_reference(mode, key, ps):
+    g = np.load(os.path.join(GOLDEN, "controllers_smpl.npz"))
+    om, _ = _om(control_mode=mode, power_scale=ps)
+    e = orc.OracleEnv(om)
+    for i in range(g["qpos"].shape[0]):
+        # forward pass at the stale state leaves M there (quirk Q1); bias is overwritten by the golden C
+        e.qpos[:] = g["qpos_stale"][i]
+        e.qvel[:] = 0
+        e.forward()
+        np.testing.assert_allclose(e.M, g["M"][i], atol=1e-11)
+        e.qfrc_bias[:] = g["C"][i]
+        e.qpos[:] = g["qpos"][i]
+        e.qvel[:] = g["qvel"][i]
+        tau = e.compute_torque(g["action"][i])
+        np.testing.assert_allclose(tau, g[key][i], rtol=1e-9, atol=1e-8)
+
+
+def test_philox_known_answer():
+    # Random123 KAT: philox4x32-10, counter 0, key 0
+    assert orc.philox(0, 0, 0) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
