@@ -1,0 +1,254 @@
+// smplsim_capi.cu -- extern "C" boundary of libsmplsim_b200.so (see include/smplsim.h).
+// Host side: float32 image of the model table, tree schedule, shared-memory layout, launches.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "env_kernels.cuh"
+
+struct SmplsimHandle {
+  DevModel hm;        // host copy
+  DevModel* dm;       // device copy
+  EnvLayout lay;
+  int num_envs, device, wpb;
+  size_t smem_bytes;
+};
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                                     \
+  do {                                                                                                  \
+    cudaError_t e_ = (x);                                                                               \
+    if (e_ != cudaSuccess) return fail(SMPLSIM_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" const char* smplsim_last_error(void) { return g_err.c_str(); }
+extern "C" int smplsim_version(void) { return 100; }
+
+static EnvLayout make_layout(const DevModel& m) {
+  EnvLayout L;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };   // 16-byte aligned sections
+  int nb = m.nb, nv = m.nv, nq = m.nq, nu = m.nu, ns = m.nslot;
+  L.qpos = take(nq); L.qvel = take(nv); L.act = take(nu); L.tau = take(nu); L.qacc = take(nv); L.qwarm = take(nv);
+  L.xpos = take(3 * nb); L.xquat = take(4 * nb); L.xmat = take(9 * nb); L.ax = take(3 * nv); L.vel = take(6 * nb);
+  L.abias = take(6 * nb); L.pb = take(6 * nb); L.irb = take(10 * nb); L.IA = take(21 * nb); L.pA = take(6 * nb);
+  L.U = take(6 * nv); L.Dinv = take(nv); L.u = take(nv); L.acc = take(6 * nb);
+  L.spd_ax = take(3 * nv); L.spd_xpos = take(3 * nb); L.spd_U = take(6 * nv); L.spd_Dinv = take(nv); L.spd_ab = take(nv);
+  L.tin = take(nv); L.dadd = take(nv); L.qstar = take(nv); L.tsk = take(8);
+  L.lD = take(nv); L.laref = take(nv); L.lr = take(nv); L.lphi = take(nv); L.lrs = take(nv); L.lflag = take(nv);
+  L.cpos = take(3 * ns); L.ct1 = take(3 * ns); L.cD = take(ns); L.caref = take(4 * ns); L.cr = take(4 * ns);
+  L.cphi = take(4 * ns); L.crs = take(4 * ns); L.cflag = take(ns);
+  L.sens = take(6 * nb);
+  L.obs = take(m.obs_dim + 4);
+  L.total = o;
+  return L;
+}
+
+static int obs_dims(const SmplsimModelDesc* s, const SmplsimEnvCfg* c, int* self_dim) {
+  int nb = s->nbody;
+  int n = (c->root_height_obs ? 1 : 0) + 3 * (nb - 1) + 6 * nb;   // humanoid_env.py:293-299
+  n += (c->self_obs_v == 1) ? 3 + 3 + s->nu : 6 * nb;
+  *self_dim = n;
+  if (c->task == SMPLSIM_TASK_SPEED || c->task == SMPLSIM_TASK_REACH) n += 3;
+  if (c->task == SMPLSIM_TASK_GETUP) n += 1;
+  return n;
+}
+
+extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cfg, int num_envs, int cuda_device, SmplsimHandle** out) {
+  if (!s || !cfg || !out || num_envs <= 0) return fail(SMPLSIM_EINVAL, "smplsim_create: null argument or num_envs <= 0");
+  if (s->nbody > SM_MAXB || s->nv > SM_MAXV || s->ngeom > SM_MAXG || s->nbody < 1)
+    return fail(SMPLSIM_EUNSUPPORTED, "model exceeds compiled limits (bodies<=64, dofs<=192, geoms<=64)");
+  if (s->nq != s->nv + 1 || s->nu != s->nv - 6 || s->body_dofnum[0] != 6 || s->body_parent[0] != -1)
+    return fail(SMPLSIM_EUNSUPPORTED, "model class: one tree rooted at a free joint, hinge joints elsewhere");
+  if (cfg->self_obs_v != 1 && cfg->self_obs_v != 2) return fail(SMPLSIM_EINVAL, "self_obs_v must be 1 or 2");
+  if (cfg->control_mode < 0 || cfg->control_mode > 2) return fail(SMPLSIM_EINVAL, "control_mode must be uhc_pd|pd|torque");
+  if (cfg->task < 0 || cfg->task > 3) return fail(SMPLSIM_EINVAL, "unknown task");
+  if (cfg->nsubsteps < 1) return fail(SMPLSIM_EINVAL, "nsubsteps < 1");
+  SmplsimHandle* h = new SmplsimHandle();
+  DevModel& m = h->hm;
+  std::memset(&m, 0, sizeof m);
+  m.nb = s->nbody; m.nq = s->nq; m.nv = s->nv; m.nu = s->nu; m.ng = s->ngeom;
+  int maxd = 0;
+  for (int b = 0; b < m.nb; b++) {
+    m.parent[b] = s->body_parent[b]; m.dofadr[b] = s->body_dofadr[b]; m.dofnum[b] = s->body_dofnum[b];
+    if (b > 0 && (m.parent[b] < 0 || m.parent[b] >= b)) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "bodies must be listed parent-first"); }
+    if (b > 0 && m.dofnum[b] > 3) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "more than 3 hinges on a body"); }
+    m.depth[b] = b == 0 ? 0 : m.depth[m.parent[b]] + 1;
+    if (m.depth[b] > maxd) maxd = m.depth[b];
+    for (int k = 0; k < 3; k++) { m.bpos[b][k] = (float)s->body_pos[3 * b + k]; m.ipos[b][k] = (float)s->body_ipos[3 * b + k]; }
+    for (int k = 0; k < 4; k++) m.bquat[b][k] = (float)s->body_quat[4 * b + k];
+    for (int k = 0; k < 6; k++) m.inertia[b][k] = (float)s->body_inertia[6 * b + k];
+    m.mass[b] = (float)s->body_mass[b];
+    m.tran_iw0[b] = (float)s->body_invweight0[2 * b];
+    for (int k = 0; k < m.dofnum[b]; k++) m.dof_body[m.dofadr[b] + k] = b;
+  }
+  m.nlevel = maxd + 1;
+  if (m.nlevel > SM_MAXL) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "tree deeper than 16 levels"); }
+  { int o = 0; for (int l = 0; l < m.nlevel; l++) { m.level_adr[l] = o; for (int b = 0; b < m.nb; b++) if (m.depth[b] == l) m.level_list[o++] = b; } m.level_adr[m.nlevel] = o; }
+  { int o = 0; for (int b = 0; b < m.nb; b++) { m.child_adr[b] = o; for (int c = b + 1; c < m.nb; c++) if (m.parent[c] == b) m.child_list[o++] = c; } m.child_adr[m.nb] = o; }
+  for (int d = 0; d < m.nv; d++) {
+    for (int k = 0; k < 3; k++) m.axis[d][k] = (float)s->dof_axis[3 * d + k];
+    m.arm[d] = (float)s->dof_armature[d]; m.diw0[d] = (float)s->dof_invweight0[d];
+    m.range[d][0] = (float)s->dof_range[2 * d]; m.range[d][1] = (float)s->dof_range[2 * d + 1];
+    m.limited[d] = s->dof_limited[d];
+  }
+  int ns = 0;
+  m.legal_mask = 1ull;
+  for (int g = 0; g < m.ng; g++) {
+    m.gtype[g] = s->geom_type[g]; m.gbody[g] = s->geom_body[g];
+    int mc = m.gtype[g] == SMPLSIM_GEOM_BOX ? 4 : m.gtype[g] == SMPLSIM_GEOM_CAPSULE ? 2 : m.gtype[g] == SMPLSIM_GEOM_SPHERE ? 1 : -1;
+    if (mc < 0 || m.gbody[g] < 0 || m.gbody[g] >= m.nb) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "geom type (box|capsule|sphere) / body"); }
+    m.slot_adr[g] = ns;
+    for (int k = 0; k < mc; k++) { if (ns >= SM_MAXSLOT) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "too many contact slots"); } m.slot_geom[ns++] = g; }
+    for (int k = 0; k < 3; k++) { m.gpos[g][k] = (float)s->geom_pos[3 * g + k]; m.gsize[g][k] = (float)s->geom_size[3 * g + k]; }
+    for (int k = 0; k < 9; k++) m.gmat[g][k] = (float)s->geom_mat[9 * g + k];
+    if (s->geom_legal[g]) m.legal_mask |= 1ull << (g + 1);
+  }
+  m.slot_adr[m.ng] = ns; m.nslot = ns;
+  { int o = 0; for (int b = 0; b < m.nb; b++) { m.bgeom_adr[b] = o; for (int g = 0; g < m.ng; g++) if (m.gbody[g] == b) m.bgeom_list[o++] = g; } m.bgeom_adr[m.nb] = o; }
+  double nn = std::sqrt(s->plane_normal[0] * s->plane_normal[0] + s->plane_normal[1] * s->plane_normal[1] + s->plane_normal[2] * s->plane_normal[2]);
+  double n[3] = {s->plane_normal[0] / nn, s->plane_normal[1] / nn, s->plane_normal[2] / nn};
+  for (int k = 0; k < 3; k++) { m.plane_pos[k] = (float)s->plane_pos[k]; m.plane_n[k] = (float)n[k]; m.grav[k] = (float)s->gravity[k]; }
+  { // mju_makeFrame default tangent for this normal
+    double t[3] = {0, 0, 0};
+    if (n[1] < 0.5 && n[1] > -0.5) t[1] = 1; else t[2] = 1;
+    double d = n[0] * t[0] + n[1] * t[1] + n[2] * t[2];
+    for (int k = 0; k < 3; k++) t[k] -= d * n[k];
+    double tn = std::sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+    for (int k = 0; k < 3; k++) m.t1_default[k] = (float)(t[k] / tn);
+  }
+  m.margin = (float)s->margin; m.mu = (float)s->friction[0]; m.impratio = (float)s->impratio;
+  for (int k = 0; k < 5; k++) m.solimp[k] = (float)s->solimp[k];
+  { double mid = s->solimp[3], pw = s->solimp[4];
+    m.imp_a = (float)(1.0 / std::pow(mid, pw - 1)); m.imp_b = (float)(1.0 / std::pow(1 - mid, pw - 1)); }
+  { double dmax = s->solimp[1], tc = s->solref[0], dr = s->solref[1];
+    if (tc <= 0) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "direct solref (negative) is not supported"); }
+    if (tc < 2 * s->timestep) tc = 2 * s->timestep;   // refsafe
+    m.K = (float)(1.0 / std::fmax(1e-15, dmax * dmax * tc * tc * dr * dr)); m.B = (float)(2.0 / std::fmax(1e-15, dmax * tc)); }
+  m.h = (float)s->timestep;
+  for (int i = 0; i < m.nu; i++) {
+    m.kp[i] = (float)s->act_kp[i]; m.kd[i] = (float)s->act_kd[i]; m.tlim[i] = (float)s->act_torque_lim[i];
+    m.ascale[i] = (float)s->act_scale[i]; m.aoffset[i] = (float)s->act_offset[i];
+  }
+  m.cfg = *cfg;
+  if (cfg->task == SMPLSIM_TASK_REACH && (cfg->reach_body < 0 || cfg->reach_body >= m.nb)) { delete h; return fail(SMPLSIM_EINVAL, "reach_body out of range"); }
+  m.obs_dim = obs_dims(s, cfg, &m.self_obs_dim);
+  h->lay = make_layout(m);
+  h->num_envs = num_envs; h->device = cuda_device;
+  h->wpb = SM_WARPS_PER_BLOCK;
+  cudaError_t e = cudaSetDevice(cuda_device);
+  if (e != cudaSuccess) { delete h; return fail(SMPLSIM_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cuda_device);
+  while (h->wpb > 1 && (size_t)h->wpb * h->lay.total * 4 > (size_t)max_smem) h->wpb >>= 1;
+  h->smem_bytes = (size_t)h->wpb * h->lay.total * 4;
+  if (h->smem_bytes > (size_t)max_smem) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "per-env scratch exceeds shared memory"); }
+  e = cudaMalloc(&h->dm, sizeof(DevModel));
+  if (e == cudaSuccess) e = cudaMemcpy(h->dm, &m, sizeof(DevModel), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kinematics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  if (e != cudaSuccess) { if (h->dm) cudaFree(h->dm); delete h; return fail(SMPLSIM_ECUDA, std::string("smplsim_create: ") + cudaGetErrorString(e)); }
+  *out = h;
+  return SMPLSIM_OK;
+}
+
+extern "C" int smplsim_destroy(SmplsimHandle* h) {
+  if (!h) return SMPLSIM_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->dm);
+  delete h;
+  return SMPLSIM_OK;
+}
+extern "C" int smplsim_obs_dim(const SmplsimHandle* h) { return h ? h->hm.obs_dim : SMPLSIM_EINVAL; }
+extern "C" int smplsim_num_envs(const SmplsimHandle* h) { return h ? h->num_envs : SMPLSIM_EINVAL; }
+extern "C" int smplsim_smem_bytes_per_env(const SmplsimHandle* h) { return h ? h->lay.total * 4 : SMPLSIM_EINVAL; }
+extern "C" int smplsim_warps_per_block(const SmplsimHandle* h) { return h ? h->wpb : SMPLSIM_EINVAL; }
+
+static bool state_ok(const SmplsimState* st) {
+  return st && st->qpos && st->qvel && st->qpos_fwd && st->qvel_fwd && st->qacc_warm && st->task_target && st->task_change_step &&
+         st->progress && st->recovery && st->rng_counter;
+}
+static dim3 grid_for(const SmplsimHandle* h, int n) { return dim3((n + h->wpb - 1) / h->wpb); }
+
+extern "C" int smplsim_step(SmplsimHandle* h, const SmplsimState* st, const float* action_dev, float* obs_dev, float* reward_dev,
+                            uint8_t* terminated_dev, uint8_t* truncated_dev, const SmplsimAux* aux, void* stream) {
+  if (!h || !state_ok(st) || !action_dev) return fail(SMPLSIM_EINVAL, "smplsim_step: null handle/state/action");
+  StepArgs a; std::memset(&a, 0, sizeof a);
+  a.st = *st; if (aux) a.aux = *aux;
+  a.action = action_dev; a.obs = obs_dev; a.reward = reward_dev; a.terminated = terminated_dev; a.truncated = truncated_dev;
+  a.n = h->num_envs; a.nsub = h->hm.cfg.nsubsteps; a.mode = 0;
+  k_step<<<grid_for(h, a.n), 32 * h->wpb, h->smem_bytes, (cudaStream_t)stream>>>(h->dm, h->lay, a);
+  CUDA_TRY(cudaGetLastError());
+  return SMPLSIM_OK;
+}
+
+extern "C" int smplsim_mj_step(SmplsimHandle* h, const SmplsimState* st, const float* ctrl_dev, int nsub, const SmplsimAux* aux, void* stream) {
+  if (!h || !state_ok(st) || !ctrl_dev || nsub < 1) return fail(SMPLSIM_EINVAL, "smplsim_mj_step: bad argument");
+  StepArgs a; std::memset(&a, 0, sizeof a);
+  a.st = *st; if (aux) a.aux = *aux;
+  a.action = ctrl_dev; a.n = h->num_envs; a.nsub = nsub; a.mode = 1;
+  k_step<<<grid_for(h, a.n), 32 * h->wpb, h->smem_bytes, (cudaStream_t)stream>>>(h->dm, h->lay, a);
+  CUDA_TRY(cudaGetLastError());
+  return SMPLSIM_OK;
+}
+
+extern "C" int smplsim_reset(SmplsimHandle* h, const SmplsimState* st, const uint8_t* mask_dev, int init_mode, const float* qpos0_dev,
+                             const float* qvel0_dev, float* obs_dev, const SmplsimAux* aux, void* stream) {
+  if (!h || !state_ok(st)) return fail(SMPLSIM_EINVAL, "smplsim_reset: null handle/state");
+  int mode = init_mode < 0 ? h->hm.cfg.state_init : init_mode;
+  if (mode < 0 || mode > 2) return fail(SMPLSIM_EINVAL, "smplsim_reset: init_mode");
+  if (mode == SMPLSIM_INIT_MOCAP && (!qpos0_dev || !qvel0_dev)) return fail(SMPLSIM_EINVAL, "smplsim_reset: MoCap init needs qpos0/qvel0");
+  ResetArgs a; std::memset(&a, 0, sizeof a);
+  a.st = *st; if (aux) a.aux = *aux;
+  a.mask = mask_dev; a.qpos0 = qpos0_dev; a.qvel0 = qvel0_dev; a.obs = obs_dev; a.n = h->num_envs; a.init_mode = mode;
+  k_reset<<<grid_for(h, a.n), 32 * h->wpb, h->smem_bytes, (cudaStream_t)stream>>>(h->dm, h->lay, a);
+  CUDA_TRY(cudaGetLastError());
+  return SMPLSIM_OK;
+}
+
+extern "C" int smplsim_kinematics(SmplsimHandle* h, const float* qpos_dev, float* xpos_dev, float* xquat_dev, int n, void* stream) {
+  if (!h || !qpos_dev || !xpos_dev || !xquat_dev || n < 0) return fail(SMPLSIM_EINVAL, "smplsim_kinematics: bad argument");
+  if (n == 0) return SMPLSIM_OK;
+  k_kinematics<<<grid_for(h, n), 32 * h->wpb, h->smem_bytes, (cudaStream_t)stream>>>(h->dm, h->lay, qpos_dev, xpos_dev, xquat_dev, n);
+  CUDA_TRY(cudaGetLastError());
+  return SMPLSIM_OK;
+}
+
+extern "C" int smplsim_self_obs(SmplsimHandle* h, int version, const float* qvel_dev, const float* xpos_dev, const float* xquat_dev,
+                                const float* linvel_dev, const float* angvel_dev, float* obs_dev, int n, void* stream) {
+  if (!h || !xpos_dev || !xquat_dev || !obs_dev || n < 0) return fail(SMPLSIM_EINVAL, "smplsim_self_obs: bad argument");
+  if (version == 1 && !qvel_dev) return fail(SMPLSIM_EINVAL, "smplsim_self_obs: v1 needs qvel");
+  if (version == 2 && (!linvel_dev || !angvel_dev)) return fail(SMPLSIM_EINVAL, "smplsim_self_obs: v2 needs body velocities");
+  if (version != 1 && version != 2) return fail(SMPLSIM_EINVAL, "smplsim_self_obs: version");
+  if (n == 0) return SMPLSIM_OK;
+  int nb = h->hm.nb;
+  int self_dim = (h->hm.cfg.root_height_obs ? 1 : 0) + 3 * (nb - 1) + 6 * nb + (version == 1 ? 6 + h->hm.nu : 6 * nb);
+  int wpb = 4;
+  k_self_obs<<<(n + wpb - 1) / wpb, 32 * wpb, wpb * 16 * SM_MAXB * 4, (cudaStream_t)stream>>>(h->dm, version, qvel_dev, xpos_dev, xquat_dev,
+                                                                                            linvel_dev, angvel_dev, obs_dev, n, self_dim);
+  CUDA_TRY(cudaGetLastError());
+  return SMPLSIM_OK;
+}
+
+extern "C" int smplsim_motion_gather(SmplsimHandle* h, const int32_t* motion_ids_dev, const float* motion_times_dev, int n,
+                                     const float* motion_len_dev, const int32_t* num_frames_dev, const float* motion_dt_dev,
+                                     const int32_t* length_starts_dev, int num_tables, const float* const* tables_dev,
+                                     const int32_t* widths, float* const* outs_dev, int32_t* frame_idx_dev, void* stream) {
+  if (!motion_ids_dev || !motion_times_dev || !motion_len_dev || !num_frames_dev || !motion_dt_dev || !length_starts_dev || n < 0)
+    return fail(SMPLSIM_EINVAL, "smplsim_motion_gather: null argument");
+  if (num_tables < 0 || num_tables > SM_MAXTABLES) return fail(SMPLSIM_EINVAL, "smplsim_motion_gather: at most 16 tables");
+  if (n == 0) return SMPLSIM_OK;
+  (void)h;
+  GatherArgs a; std::memset(&a, 0, sizeof a);
+  a.ids = motion_ids_dev; a.times = motion_times_dev; a.mlen = motion_len_dev; a.nframes = num_frames_dev; a.mdt = motion_dt_dev;
+  a.starts = length_starts_dev; a.frame_idx = frame_idx_dev; a.n = n; a.ntab = num_tables;
+  for (int k = 0; k < num_tables; k++) { a.tables[k] = tables_dev[k]; a.outs[k] = outs_dev[k]; a.widths[k] = widths[k]; }
+  int wpb = 8;
+  k_motion_gather<<<(n + wpb - 1) / wpb, 32 * wpb, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return SMPLSIM_OK;
+}
