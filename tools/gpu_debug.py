@@ -43,7 +43,7 @@ def main():
     for mode in ("torque", "uhc_pd"):
         cfg, om = make_models(control_mode=mode)
         n = 48
-        q, v, w = rollout_states(om, n, seed=11)
+        q, v, w = rollout_states(make_models(control_mode="uhc_pd")[1], n, seed=11)
         env = HumanoidBatchB200(cfg, num_envs=n)
         ctrl = np.random.default_rng(2).uniform(-80, 80, (n, m.nu))
         env.set_state(T(q), T(v)); env.qacc_warm.copy_(T(w)); env.mj_step(T(ctrl), 1)
