@@ -15,7 +15,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 def sources():
-    return [os.path.join(_CSRC, f) for f in ("smplsim_capi.cu", "env_kernels.cuh", "physics.cuh", "dev_model.cuh")] + [
+    return [os.path.join(_CSRC, f) for f in ("smplsim_capi.cu", "env_kernels.cuh", "physics.cuh", "dev_model.cuh", "chain_kernels.cuh", "chain_model.cuh",
+                                                    "chain_host.hpp")] + [
         os.path.join(_HERE, "..", "include", "smplsim.h")]
 
 
@@ -45,9 +46,12 @@ _SYMBOLS = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "smplsim_smem_bytes_per_env": (C.c_int, [C.c_void_p]),
     "smplsim_warps_per_block": (C.c_int, [C.c_void_p]),
+    "smplsim_kernel_version": (C.c_int, [C.c_void_p]),
+    "smplsim_schedule_steps": (C.c_int, [C.c_void_p]),
 }
 # the entry points include/smplsim.h declares (checked by tests/test_abi.py)
-HEADER_SYMBOLS = [s for s in _SYMBOLS if s not in ("smplsim_smem_bytes_per_env", "smplsim_warps_per_block")]
+_INTROSPECTION = ("smplsim_smem_bytes_per_env", "smplsim_warps_per_block", "smplsim_kernel_version", "smplsim_schedule_steps")
+HEADER_SYMBOLS = [s for s in _SYMBOLS if s not in _INTROSPECTION]
 
 
 def lib():

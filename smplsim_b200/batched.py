@@ -178,6 +178,15 @@ class HumanoidBatchB200:
     def smem_bytes_per_env(self):
         return _lib.lib().smplsim_smem_bytes_per_env(self._h)
 
+    @property
+    def kernel_version(self) -> int:
+        """2: chain-lane kernels (4 lanes per env); 1: generic warp-per-env kernels (SMPLSIM_KERNEL=v1 forces them)."""
+        return _lib.lib().smplsim_kernel_version(self._h)
+
+    @property
+    def schedule_steps(self) -> int:
+        return _lib.lib().smplsim_schedule_steps(self._h)
+
 
 class GymVectEnvB200:
     """``GymVectEnv`` (smpl_sim/envs/nv/gymwrapper.py:7-65) over a HumanoidBatchB200: gymnasium-vector style

@@ -7,6 +7,10 @@
 #include <vector>
 
 #include "env_kernels.cuh"
+#include "chain_kernels.cuh"
+#include "chain_host.hpp"
+#include "warp_kernels.cuh"
+#include <cstdlib>
 
 struct SmplsimHandle {
   DevModel hm;        // host copy
@@ -14,7 +18,71 @@ struct SmplsimHandle {
   EnvLayout lay;
   int num_envs, device, wpb;
   size_t smem_bytes;
+  // v2 (chain-lane kernels)
+  bool v2 = false;
+  int tmax = 0, wpb2 = 4;
+  ChainEntry* d_tab = nullptr;
+  ChainConsts kc;
+  size_t smem2 = 0;
+  std::string v2_why;
+  // v3 (level-synchronous, compile-time layout): cls 0 none, 1 SMPL lpe32, 2 SMPL lpe16, 3 SMPL-X, 4 generic
+  int v3cls = 0, wpb3 = 4;
+  size_t smem3 = 0;
 };
+
+typedef WCfg<24, 75, 24, 64, 32> WC_SMPL32;
+typedef WCfg<24, 75, 24, 64, 16> WC_SMPL16;
+typedef WCfg<52, 159, 52, 120, 32> WC_SMPLX;
+typedef WCfg<64, 192, 64, 128, 32> WC_GEN;
+
+template <class C>
+static int v3_configure(SmplsimHandle* h) {
+  constexpr size_t mbytes = ((sizeof(WModel<C>) + 15) / 16) * 16;
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+  int best_w = 0, best_wpb = 0;
+  const int cand[] = {16, 14, 12, 8, 7, 6, 4, 3, 2, 1};
+  for (int wpb : cand) {
+    size_t sm = mbytes + (size_t)wpb * C::EPW * C::total * 4;
+    if (sm > (size_t)max_smem) continue;
+    if (cudaFuncSetAttribute(k_step3<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) continue;
+    int nblk = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, k_step3<C>, 32 * wpb, sm) != cudaSuccess) continue;
+    if (nblk * wpb > best_w) { best_w = nblk * wpb; best_wpb = wpb; }
+  }
+  if (!best_wpb) return -1;
+  h->wpb3 = best_wpb;
+  h->smem3 = mbytes + (size_t)best_wpb * C::EPW * C::total * 4;
+  if (cudaFuncSetAttribute(k_step3<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem3) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(k_reset3<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem3) != cudaSuccess) return -1;
+  return best_w;
+}
+template <class C>
+static void v3_step(SmplsimHandle* h, const WStepArgs& a, cudaStream_t st) {
+  int per = h->wpb3 * C::EPW;
+  k_step3<C><<<(a.n + per - 1) / per, 32 * h->wpb3, h->smem3, st>>>(h->dm, a);
+}
+template <class C>
+static void v3_reset(SmplsimHandle* h, const WResetArgs& a, cudaStream_t st) {
+  int per = h->wpb3 * C::EPW;
+  k_reset3<C><<<(a.n + per - 1) / per, 32 * h->wpb3, h->smem3, st>>>(h->dm, a);
+}
+static void launch_step3(SmplsimHandle* h, const WStepArgs& a, cudaStream_t st) {
+  switch (h->v3cls) {
+    case 1: v3_step<WC_SMPL32>(h, a, st); break;
+    case 2: v3_step<WC_SMPL16>(h, a, st); break;
+    case 3: v3_step<WC_SMPLX>(h, a, st); break;
+    default: v3_step<WC_GEN>(h, a, st); break;
+  }
+}
+static void launch_reset3(SmplsimHandle* h, const WResetArgs& a, cudaStream_t st) {
+  switch (h->v3cls) {
+    case 1: v3_reset<WC_SMPL32>(h, a, st); break;
+    case 2: v3_reset<WC_SMPL16>(h, a, st); break;
+    case 3: v3_reset<WC_SMPLX>(h, a, st); break;
+    default: v3_reset<WC_GEN>(h, a, st); break;
+  }
+}
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -152,6 +220,52 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kinematics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   if (e != cudaSuccess) { if (h->dm) cudaFree(h->dm); delete h; return fail(SMPLSIM_ECUDA, std::string("smplsim_create: ") + cudaGetErrorString(e)); }
+  // ---- v2: chain-lane kernels (4 lanes per env) when the model fits their schedule limits
+  {
+    const char* force = std::getenv("SMPLSIM_KERNEL");
+    ChainPlan P = chain_plan(s, CH_MAXLEDGE);
+    if (!P.ok) h->v2_why = P.why;
+    else if (P.T > 16) h->v2_why = "schedule longer than 16 steps";
+    else if (!force || std::string(force) != "v2") h->v2_why = "chain-lane kernels are opt-in (SMPLSIM_KERNEL=v2)";
+    else {
+      ChainConsts& k = h->kc;
+      std::memset(&k, 0, sizeof k);
+      k.T = P.T; k.nb = m.nb; k.nq = m.nq; k.nv = m.nv; k.nu = m.nu; k.ng = m.ng; k.n_mbox = P.n_mbox; k.n_xedge = P.n_xedge;
+      k.mb_stride = (19 * P.n_mbox + 27 * P.n_xedge + CH_SC_WORDS) | 1;
+      k.obs_dim = m.obs_dim; k.self_obs_dim = m.self_obs_dim;
+      for (int i = 0; i < 3; i++) { k.plane_pos[i] = m.plane_pos[i]; k.plane_n[i] = m.plane_n[i]; k.t1_default[i] = m.t1_default[i]; k.grav[i] = m.grav[i]; }
+      k.margin = m.margin; k.mu = m.mu; k.impratio = m.impratio;
+      for (int i = 0; i < 5; i++) k.solimp[i] = m.solimp[i];
+      k.imp_a = m.imp_a; k.imp_b = m.imp_b; k.K = m.K; k.B = m.B; k.h = m.h; k.legal_mask = m.legal_mask; k.cfg = m.cfg;
+      h->tmax = P.T <= 10 ? 10 : 16;
+      size_t tabw = (size_t)P.T * CH_LPE * (sizeof(ChainEntry) / 4);
+      h->wpb2 = 4;
+      h->smem2 = (tabw + (size_t)h->wpb2 * CH_EPW * k.mb_stride) * 4;
+      cudaError_t e2 = cudaMalloc(&h->d_tab, P.tab.size() * sizeof(ChainEntry));
+      if (e2 == cudaSuccess) e2 = cudaMemcpy(h->d_tab, P.tab.data(), P.tab.size() * sizeof(ChainEntry), cudaMemcpyHostToDevice);
+      if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_step2<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem2);
+      if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_reset2<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem2);
+      if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_step2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem2);
+      if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_reset2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem2);
+      if (e2 != cudaSuccess) { cudaFree(h->dm); if (h->d_tab) cudaFree(h->d_tab); delete h; return fail(SMPLSIM_ECUDA, std::string("smplsim_create(v2): ") + cudaGetErrorString(e2)); }
+      h->v2 = true;
+    }
+  }
+  // ---- v3: default hot path
+  {
+    const char* force = std::getenv("SMPLSIM_KERNEL");
+    const char* lpe = std::getenv("SMPLSIM_LPE");
+    bool want = !force || std::string(force) == "v3";
+    if (want && !h->v2) {
+      int cls;
+      if (m.nb <= 24 && m.nv <= 75 && m.ng <= 24 && m.nslot <= 64) cls = (lpe && std::string(lpe) == "16" && m.nlevel > 0) ? 2 : 1;
+      else if (m.nb <= 52 && m.nv <= 159 && m.ng <= 52 && m.nslot <= 120) cls = 3;
+      else cls = 4;
+      h->v3cls = cls;
+      int r = cls == 1 ? v3_configure<WC_SMPL32>(h) : cls == 2 ? v3_configure<WC_SMPL16>(h) : cls == 3 ? v3_configure<WC_SMPLX>(h) : v3_configure<WC_GEN>(h);
+      if (r < 0) h->v3cls = 0;
+    }
+  }
   *out = h;
   return SMPLSIM_OK;
 }
@@ -160,13 +274,31 @@ extern "C" int smplsim_destroy(SmplsimHandle* h) {
   if (!h) return SMPLSIM_OK;
   cudaSetDevice(h->device);
   cudaFree(h->dm);
+  if (h->d_tab) cudaFree(h->d_tab);
   delete h;
   return SMPLSIM_OK;
 }
 extern "C" int smplsim_obs_dim(const SmplsimHandle* h) { return h ? h->hm.obs_dim : SMPLSIM_EINVAL; }
 extern "C" int smplsim_num_envs(const SmplsimHandle* h) { return h ? h->num_envs : SMPLSIM_EINVAL; }
-extern "C" int smplsim_smem_bytes_per_env(const SmplsimHandle* h) { return h ? h->lay.total * 4 : SMPLSIM_EINVAL; }
-extern "C" int smplsim_warps_per_block(const SmplsimHandle* h) { return h ? h->wpb : SMPLSIM_EINVAL; }
+extern "C" int smplsim_smem_bytes_per_env(const SmplsimHandle* h) {
+  if (!h) return SMPLSIM_EINVAL;
+  switch (h->v3cls) { case 1: return WC_SMPL32::total * 4; case 2: return WC_SMPL16::total * 4; case 3: return WC_SMPLX::total * 4; case 4: return WC_GEN::total * 4; }
+  return h->lay.total * 4;
+}
+extern "C" int smplsim_warps_per_block(const SmplsimHandle* h) { return h ? (h->v3cls ? h->wpb3 : h->v2 ? h->wpb2 : h->wpb) : SMPLSIM_EINVAL; }
+/* 2: chain-lane kernels (4 lanes/env), 1: generic warp-per-env kernels; steps of the chain schedule */
+extern "C" int smplsim_kernel_version(const SmplsimHandle* h) { return h ? (h->v2 ? 2 : h->v3cls ? 3 : 1) : SMPLSIM_EINVAL; }
+extern "C" int smplsim_schedule_steps(const SmplsimHandle* h) { return h ? (h->v2 ? h->kc.T : h->hm.nlevel) : SMPLSIM_EINVAL; }
+
+static dim3 grid2(const SmplsimHandle* h, int n) { int per = h->wpb2 * CH_EPW; return dim3((n + per - 1) / per); }
+static void launch_step2(SmplsimHandle* h, const ChainStepArgs& a, cudaStream_t st) {
+  if (h->tmax == 10) k_step2<10><<<grid2(h, a.n), 32 * h->wpb2, h->smem2, st>>>(h->d_tab, h->kc, a);
+  else k_step2<16><<<grid2(h, a.n), 32 * h->wpb2, h->smem2, st>>>(h->d_tab, h->kc, a);
+}
+static void launch_reset2(SmplsimHandle* h, const ChainResetArgs& a, cudaStream_t st) {
+  if (h->tmax == 10) k_reset2<10><<<grid2(h, a.n), 32 * h->wpb2, h->smem2, st>>>(h->d_tab, h->kc, a);
+  else k_reset2<16><<<grid2(h, a.n), 32 * h->wpb2, h->smem2, st>>>(h->d_tab, h->kc, a);
+}
 
 static bool state_ok(const SmplsimState* st) {
   return st && st->qpos && st->qvel && st->qpos_fwd && st->qvel_fwd && st->qacc_warm && st->task_target && st->task_change_step &&
@@ -181,6 +313,15 @@ extern "C" int smplsim_step(SmplsimHandle* h, const SmplsimState* st, const floa
   a.st = *st; if (aux) a.aux = *aux;
   a.action = action_dev; a.obs = obs_dev; a.reward = reward_dev; a.terminated = terminated_dev; a.truncated = truncated_dev;
   a.n = h->num_envs; a.nsub = h->hm.cfg.nsubsteps; a.mode = 0;
+  if (h->v3cls) {
+    WStepArgs b; b.st = a.st; b.aux = a.aux; b.action = a.action; b.obs = a.obs; b.reward = a.reward; b.terminated = a.terminated;
+    b.truncated = a.truncated; b.n = a.n; b.nsub = a.nsub; b.mode = 0;
+    launch_step3(h, b, (cudaStream_t)stream);
+  } else if (h->v2) {
+    ChainStepArgs b; b.st = a.st; b.aux = a.aux; b.action = a.action; b.obs = a.obs; b.reward = a.reward; b.terminated = a.terminated;
+    b.truncated = a.truncated; b.n = a.n; b.nsub = a.nsub; b.mode = 0;
+    launch_step2(h, b, (cudaStream_t)stream);
+  } else
   k_step<<<grid_for(h, a.n), 32 * h->wpb, h->smem_bytes, (cudaStream_t)stream>>>(h->dm, h->lay, a);
   CUDA_TRY(cudaGetLastError());
   return SMPLSIM_OK;
@@ -191,6 +332,15 @@ extern "C" int smplsim_mj_step(SmplsimHandle* h, const SmplsimState* st, const f
   StepArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
   a.action = ctrl_dev; a.n = h->num_envs; a.nsub = nsub; a.mode = 1;
+  if (h->v3cls) {
+    WStepArgs b; std::memset(&b, 0, sizeof b);
+    b.st = a.st; b.aux = a.aux; b.action = a.action; b.n = a.n; b.nsub = a.nsub; b.mode = 1;
+    launch_step3(h, b, (cudaStream_t)stream);
+  } else if (h->v2) {
+    ChainStepArgs b; std::memset(&b, 0, sizeof b);
+    b.st = a.st; b.aux = a.aux; b.action = a.action; b.n = a.n; b.nsub = a.nsub; b.mode = 1;
+    launch_step2(h, b, (cudaStream_t)stream);
+  } else
   k_step<<<grid_for(h, a.n), 32 * h->wpb, h->smem_bytes, (cudaStream_t)stream>>>(h->dm, h->lay, a);
   CUDA_TRY(cudaGetLastError());
   return SMPLSIM_OK;
@@ -205,6 +355,13 @@ extern "C" int smplsim_reset(SmplsimHandle* h, const SmplsimState* st, const uin
   ResetArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
   a.mask = mask_dev; a.qpos0 = qpos0_dev; a.qvel0 = qvel0_dev; a.obs = obs_dev; a.n = h->num_envs; a.init_mode = mode;
+  if (h->v3cls) {
+    WResetArgs b; b.st = a.st; b.aux = a.aux; b.mask = a.mask; b.qpos0 = a.qpos0; b.qvel0 = a.qvel0; b.obs = a.obs; b.n = a.n; b.init_mode = a.init_mode;
+    launch_reset3(h, b, (cudaStream_t)stream);
+  } else if (h->v2) {
+    ChainResetArgs b; b.st = a.st; b.aux = a.aux; b.mask = a.mask; b.qpos0 = a.qpos0; b.qvel0 = a.qvel0; b.obs = a.obs; b.n = a.n; b.init_mode = a.init_mode;
+    launch_reset2(h, b, (cudaStream_t)stream);
+  } else
   k_reset<<<grid_for(h, a.n), 32 * h->wpb, h->smem_bytes, (cudaStream_t)stream>>>(h->dm, h->lay, a);
   CUDA_TRY(cudaGetLastError());
   return SMPLSIM_OK;

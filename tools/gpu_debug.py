@@ -22,7 +22,7 @@ def main():
     cfg, om = make_models(control_mode="torque")
     m = om.model
     env = HumanoidBatchB200(cfg, num_envs=16)
-    print("smem bytes/env", env.smem_bytes_per_env())
+    print("smem bytes/env", env.smem_bytes_per_env(), "kernel version", env.kernel_version, "schedule steps", env.schedule_steps)
     q, v = airborne_states(m, 16, seed=3)
     xp, xq = env.kinematics(T(q))
     e = orc.OracleEnv(om)
@@ -85,6 +85,10 @@ def main():
         a = torch.zeros(n, m.nu, device="cuda:0")
         for _ in range(3):
             env.step(a); env.reset_done()
+        torch.cuda.synchronize(); t0 = time.time()
+        g = torch.Generator(device="cuda:0"); g.manual_seed(0)
+        for _ in range(40):
+            env.step(torch.clamp(torch.randn(n, m.nu, generator=g, device="cuda:0") * 0.0821, -1, 1)); env.reset_done()
         torch.cuda.synchronize(); t0 = time.time()
         for _ in range(10):
             env.step(a); env.reset_done()
