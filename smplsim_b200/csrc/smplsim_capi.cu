@@ -26,12 +26,13 @@ struct SmplsimHandle {
   size_t smem2 = 0;
   std::string v2_why;
   // v3 (level-synchronous, compile-time layout): cls 0 none, 1 SMPL lpe32, 2 SMPL lpe16, 3 SMPL-X, 4 generic
-  int v3cls = 0, wpb3 = 4;
+  int v3cls = 0, wpb3 = 4, align3 = 1;
   size_t smem3 = 0;
 };
 
 typedef WCfg<24, 75, 24, 64, 32> WC_SMPL32;
 typedef WCfg<24, 75, 24, 64, 16> WC_SMPL16;
+typedef WCfg<24, 75, 24, 64, 8> WC_SMPL8;
 typedef WCfg<52, 159, 52, 120, 32> WC_SMPLX;
 typedef WCfg<64, 192, 64, 128, 32> WC_GEN;
 
@@ -40,9 +41,10 @@ static int v3_configure(SmplsimHandle* h) {
   constexpr size_t mbytes = ((sizeof(WModel<C>) + 15) / 16) * 16;
   int max_smem = 0;
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
-  int best_w = 0, best_wpb = 0;
+  int best_w = 0, best_wpb = 0, forced = h->wpb3;
   const int cand[] = {16, 14, 12, 8, 7, 6, 4, 3, 2, 1};
   for (int wpb : cand) {
+    if (forced > 0 && wpb != forced) continue;
     size_t sm = mbytes + (size_t)wpb * C::EPW * C::total * 4;
     if (sm > (size_t)max_smem) continue;
     if (cudaFuncSetAttribute(k_step3<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) continue;
@@ -71,6 +73,7 @@ static void launch_step3(SmplsimHandle* h, const WStepArgs& a, cudaStream_t st) 
   switch (h->v3cls) {
     case 1: v3_step<WC_SMPL32>(h, a, st); break;
     case 2: v3_step<WC_SMPL16>(h, a, st); break;
+    case 5: v3_step<WC_SMPL8>(h, a, st); break;
     case 3: v3_step<WC_SMPLX>(h, a, st); break;
     default: v3_step<WC_GEN>(h, a, st); break;
   }
@@ -79,6 +82,7 @@ static void launch_reset3(SmplsimHandle* h, const WResetArgs& a, cudaStream_t st
   switch (h->v3cls) {
     case 1: v3_reset<WC_SMPL32>(h, a, st); break;
     case 2: v3_reset<WC_SMPL16>(h, a, st); break;
+    case 5: v3_reset<WC_SMPL8>(h, a, st); break;
     case 3: v3_reset<WC_SMPLX>(h, a, st); break;
     default: v3_reset<WC_GEN>(h, a, st); break;
   }
@@ -255,14 +259,18 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   {
     const char* force = std::getenv("SMPLSIM_KERNEL");
     const char* lpe = std::getenv("SMPLSIM_LPE");
+    const char* al = std::getenv("SMPLSIM_ALIGN");
+    if (al) h->align3 = std::atoi(al);
+    const char* wp = std::getenv("SMPLSIM_WPB");
+    h->wpb3 = wp ? std::atoi(wp) : 0;
     bool want = !force || std::string(force) == "v3";
     if (want && !h->v2) {
       int cls;
-      if (m.nb <= 24 && m.nv <= 75 && m.ng <= 24 && m.nslot <= 64) cls = (lpe && std::string(lpe) == "16" && m.nlevel > 0) ? 2 : 1;
+      if (m.nb <= 24 && m.nv <= 75 && m.ng <= 24 && m.nslot <= 64) cls = (lpe && std::string(lpe) == "16") ? 2 : (lpe && std::string(lpe) == "8") ? 5 : 1;
       else if (m.nb <= 52 && m.nv <= 159 && m.ng <= 52 && m.nslot <= 120) cls = 3;
       else cls = 4;
       h->v3cls = cls;
-      int r = cls == 1 ? v3_configure<WC_SMPL32>(h) : cls == 2 ? v3_configure<WC_SMPL16>(h) : cls == 3 ? v3_configure<WC_SMPLX>(h) : v3_configure<WC_GEN>(h);
+      int r = cls == 1 ? v3_configure<WC_SMPL32>(h) : cls == 2 ? v3_configure<WC_SMPL16>(h) : cls == 5 ? v3_configure<WC_SMPL8>(h) : cls == 3 ? v3_configure<WC_SMPLX>(h) : v3_configure<WC_GEN>(h);
       if (r < 0) h->v3cls = 0;
     }
   }
@@ -282,7 +290,7 @@ extern "C" int smplsim_obs_dim(const SmplsimHandle* h) { return h ? h->hm.obs_di
 extern "C" int smplsim_num_envs(const SmplsimHandle* h) { return h ? h->num_envs : SMPLSIM_EINVAL; }
 extern "C" int smplsim_smem_bytes_per_env(const SmplsimHandle* h) {
   if (!h) return SMPLSIM_EINVAL;
-  switch (h->v3cls) { case 1: return WC_SMPL32::total * 4; case 2: return WC_SMPL16::total * 4; case 3: return WC_SMPLX::total * 4; case 4: return WC_GEN::total * 4; }
+  switch (h->v3cls) { case 1: return WC_SMPL32::total * 4; case 2: return WC_SMPL16::total * 4; case 5: return WC_SMPL8::total * 4; case 3: return WC_SMPLX::total * 4; case 4: return WC_GEN::total * 4; }
   return h->lay.total * 4;
 }
 extern "C" int smplsim_warps_per_block(const SmplsimHandle* h) { return h ? (h->v3cls ? h->wpb3 : h->v2 ? h->wpb2 : h->wpb) : SMPLSIM_EINVAL; }
@@ -315,7 +323,7 @@ extern "C" int smplsim_step(SmplsimHandle* h, const SmplsimState* st, const floa
   a.n = h->num_envs; a.nsub = h->hm.cfg.nsubsteps; a.mode = 0;
   if (h->v3cls) {
     WStepArgs b; b.st = a.st; b.aux = a.aux; b.action = a.action; b.obs = a.obs; b.reward = a.reward; b.terminated = a.terminated;
-    b.truncated = a.truncated; b.n = a.n; b.nsub = a.nsub; b.mode = 0;
+    b.truncated = a.truncated; b.n = a.n; b.nsub = a.nsub; b.mode = 0; b.align = h->align3;
     launch_step3(h, b, (cudaStream_t)stream);
   } else if (h->v2) {
     ChainStepArgs b; b.st = a.st; b.aux = a.aux; b.action = a.action; b.obs = a.obs; b.reward = a.reward; b.terminated = a.terminated;
@@ -334,7 +342,7 @@ extern "C" int smplsim_mj_step(SmplsimHandle* h, const SmplsimState* st, const f
   a.action = ctrl_dev; a.n = h->num_envs; a.nsub = nsub; a.mode = 1;
   if (h->v3cls) {
     WStepArgs b; std::memset(&b, 0, sizeof b);
-    b.st = a.st; b.aux = a.aux; b.action = a.action; b.n = a.n; b.nsub = a.nsub; b.mode = 1;
+    b.st = a.st; b.aux = a.aux; b.action = a.action; b.n = a.n; b.nsub = a.nsub; b.mode = 1; b.align = h->align3;
     launch_step3(h, b, (cudaStream_t)stream);
   } else if (h->v2) {
     ChainStepArgs b; std::memset(&b, 0, sizeof b);
