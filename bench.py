@@ -265,6 +265,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": N, "global_envs": total_envs, "substeps_per_step": int(env.envcfg.nsubsteps),
                        "control_mode": "uhc_pd", "spd_inertia": "stale" if env.envcfg.spd_stale else "fresh", "parallelism": f"env-shard x{world}",
+                       "kernel": f"v{env.kernel_version}", "smem_bytes_per_env": env.smem_bytes_per_env(),
                        "l2": "256 MiB flush buffer zeroed after every step inside the timed region (state ~11 MB < 126 MB L2)"},
             "substeps_per_s": value * int(env.envcfg.nsubsteps),
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": N * nu * 4, "d2h_bytes_per_step": N * (env.num_obs * 4 + 4 + 2),

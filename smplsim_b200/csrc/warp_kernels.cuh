@@ -699,7 +699,7 @@ struct WStepArgs {
   uint8_t* terminated;
   uint8_t* truncated;
   int n, nsub, mode;
-  int align;   // 1: CTA barrier at every substep (phase alignment for the instruction cache)
+  int align;   // P > 0: CTA barrier every P substeps (phase alignment for the instruction cache); 0: none
 };
 struct WResetArgs {
   SmplsimState st;
@@ -757,13 +757,13 @@ struct WFwd { unsigned long long mask; int iters; };
 
 template <class C>
 __device__ __noinline__ float w_substeps(const WModel<C>& M, float* sm, const WLane& w, int nsub, int raw, WFwd* fo, const SmplsimState& st, int env,
-                                         bool write_fwd, bool prep_last, bool align) {
+                                         bool write_fwd, bool prep_last, int align) {
   const bool spd = (M.cfg.control_mode == SMPLSIM_CTRL_UHC_PD), stale = M.cfg.spd_stale != 0;
   float disp = 0.f;
   for (int s = 0; s < nsub; s++) {
     // keep the warps of a CTA in the same phase: the hot code of one phase fits the instruction cache, that of
     // 14 drifting warps does not (round-1 profile: "no_instruction" was the top stall)
-    if (align) __syncthreads();
+    if (align > 0 && (s % align) == 0) __syncthreads();
     bool did_fk = false;
     if (!raw) {
       if (spd && !stale) { w_fk(M, sm, w, true); w_spd_prepare(M, sm, w); did_fk = true; }
@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(512) k_step3(const DevModel* __restrict__ G, W
   }
   __syncwarp();
   WFwd fo; fo.mask = 0ull; fo.iters = 0;
-  float disp = w_substeps(M, sm, w, a.nsub, a.mode, &fo, a.st, env, true, false, a.align != 0);
+  float disp = w_substeps(M, sm, w, a.nsub, a.mode, &fo, a.st, env, true, false, a.align);
   w_fk(M, sm, w, false);
   if (a.mode == 0) {
     int* ti = (int*)(sm + C::tsk);
@@ -998,7 +998,7 @@ __global__ void __launch_bounds__(512) k_reset3(const DevModel* __restrict__ G, 
       __syncwarp();
       if (w.live && w.li == 0) ti[W_TSK_RNG] = (int)(base + (uint32_t)ngrp);
       __syncwarp();
-      w_substeps(M, sm, w, c.nsubsteps, 0, &fo, a.st, env, false, true, false);
+      w_substeps(M, sm, w, c.nsubsteps, 0, &fo, a.st, env, false, true, 0);
     }
   }
   // reset_sim(): mj_forward at the reset state
