@@ -15,6 +15,7 @@
 #define SM_MAXL 16    // tree levels
 #define SM_MAXSLOT 128 // contact slots (sum over geoms of max contacts)
 #define SM_WARPS_PER_BLOCK 4
+#define SM_MAXSCHED 20
 
 struct DevModel {
   int nb, nq, nv, nu, ng, nlevel, nslot;
@@ -38,6 +39,9 @@ struct DevModel {
   float kp[SM_MAXV], kd[SM_MAXV], tlim[SM_MAXV], ascale[SM_MAXV], aoffset[SM_MAXV];
   SmplsimEnvCfg cfg;
   int obs_dim, self_obs_dim;
+  int rowpar;                           // 1: row-parallel sweeps (8 lanes per body) when LPE == 32
+  int sched_T, sched[SM_MAXSCHED][4];   // 4-slot list schedule of the inward sweep (row-parallel kernels); sched_T = 0: none
+  int sched_nd[SM_MAXSCHED], sched_nc[SM_MAXSCHED], sched_ns[SM_MAXSCHED];  // per step: max dofs / children / contact slots (uniform loop bounds)
 };
 
 // Per-env scratch in shared memory: offsets (in 4-byte words) computed on the host.

@@ -11,6 +11,7 @@
 #include "chain_host.hpp"
 #include "warp_kernels.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 struct SmplsimHandle {
   DevModel hm;        // host copy
@@ -208,6 +209,38 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   m.cfg = *cfg;
   if (cfg->task == SMPLSIM_TASK_REACH && (cfg->reach_body < 0 || cfg->reach_body >= m.nb)) { delete h; return fail(SMPLSIM_EINVAL, "reach_body out of range"); }
   m.obs_dim = obs_dims(s, cfg, &m.self_obs_dim);
+  { // 4-slot list schedule of the inward sweep: children strictly before parents, deepest bodies first
+    std::vector<int> step(m.nb, -1);
+    int done = 0, t = 0;
+    m.sched_T = 0;
+    while (done < m.nb && t < SM_MAXSCHED) {
+      std::vector<int> ready;
+      for (int b = 0; b < m.nb; b++) {
+        if (step[b] >= 0) continue;
+        bool ok = true;
+        for (int ci = m.child_adr[b]; ci < m.child_adr[b + 1]; ci++) { int c = m.child_list[ci]; if (step[c] < 0 || step[c] >= t) ok = false; }
+        if (ok) ready.push_back(b);
+      }
+      std::sort(ready.begin(), ready.end(), [&](int a, int b2) { return m.depth[a] != m.depth[b2] ? m.depth[a] > m.depth[b2] : a < b2; });
+      for (int k = 0; k < 4; k++) m.sched[t][k] = k < (int)ready.size() ? ready[k] : -1;
+      for (int k = 0; k < 4 && k < (int)ready.size(); k++) { step[ready[k]] = t; done++; }
+      t++;
+    }
+    if (done == m.nb) m.sched_T = t;
+    for (int b = 0; b < m.nb; b++) if (m.bgeom_adr[b + 1] - m.bgeom_adr[b] > 1) m.sched_T = 0;   // row-parallel path: one geom per body
+    for (int tt = 0; tt < m.sched_T; tt++) {
+      int nd = 0, nc = 0, ns = 0;
+      for (int k = 0; k < 4; k++) {
+        int b = m.sched[tt][k];
+        if (b < 0) continue;
+        nd = std::max(nd, m.dofnum[b]); nc = std::max(nc, m.child_adr[b + 1] - m.child_adr[b]);
+        if (m.bgeom_adr[b + 1] > m.bgeom_adr[b]) { int g = m.bgeom_list[m.bgeom_adr[b]]; ns = std::max(ns, m.slot_adr[g + 1] - m.slot_adr[g]); }
+      }
+      m.sched_nd[tt] = nd; m.sched_nc[tt] = nc; m.sched_ns[tt] = ns;
+    }
+    const char* rp = std::getenv("SMPLSIM_ROWS");
+    m.rowpar = rp ? std::atoi(rp) : 0;   // opt-in: measured slower than the level sweeps in round 1 (profiles/r1_k_step3_rows.md)
+  }
   h->lay = make_layout(m);
   h->num_envs = num_envs; h->device = cuda_device;
   h->wpb = SM_WARPS_PER_BLOCK;

@@ -28,7 +28,7 @@ struct WCfg {
   // per-env scratch (words)
   static constexpr int qpos = 0, qvel = qpos + r4(NQ), act = qvel + r4(NV), tau = act + r4(NU), qacc = tau + r4(NU), qstar = qacc + r4(NV),
                        spdab = qstar + r4(NV), xpos = spdab + r4(NV), xquat = xpos + r4(3 * NB), ax = xquat + r4(4 * NB), vel = ax + r4(3 * NV),
-                       pb = vel + r4(6 * NB), IA = pb + r4(6 * NB), pA = IA + r4(21 * NB), U = pA + r4(6 * NB), Dinv = U + r4(6 * NV),
+                       pb = vel + r4(6 * NB), irb = pb + r4(6 * NB), IA = irb + r4(10 * NB), pA = IA + r4(21 * NB), U = pA + r4(6 * NB), Dinv = U + r4(6 * NV),
                        u = Dinv + r4(NV), acc = u + r4(NV), acc2 = acc + r4(6 * NB), cpos = acc2 + r4(6 * NB), cD = cpos + r4(3 * NS),
                        caref = cD + r4(NS), cphi = caref + r4(4 * NS), cflag = cphi + r4(4 * NS), ct1 = cflag + r4(NS), lim = ct1 + r4(3 * NG),
                        tsk = lim + r4(8 * W_MAXLIM + 4), total_ = tsk + 12;
@@ -40,7 +40,8 @@ struct WCfg {
 // constants staged per CTA (float32 image of the model, exact sizes)
 template <class C>
 struct WModel {
-  int nb, nv, nu, ng, nlevel, nslot;
+  int nb, nv, nu, ng, nlevel, nslot, sched_T, rowpar;
+  int sched[SM_MAXSCHED][4], sched_nd[SM_MAXSCHED], sched_nc[SM_MAXSCHED], sched_ns[SM_MAXSCHED];
   int parent[C::NB], dofadr[C::NB], dofnum[C::NB];
   int level_adr[SM_MAXL + 1], level_list[C::NB], child_adr[C::NB + 1], child_list[C::NB];
   int bgeom_adr[C::NB + 1], bgeom_list[C::NG], gtype[C::NG], gbody[C::NG], slot_adr[C::NG + 1], slot_geom[C::NS], limited[C::NV];
@@ -65,6 +66,11 @@ __device__ void w_stage_model(const DevModel* __restrict__ G, WModel<C>& M) {
     for (int i = 0; i < 5; i++) M.solimp[i] = G->solimp[i];
     M.imp_a = G->imp_a; M.imp_b = G->imp_b; M.K = G->K; M.B = G->B; M.h = G->h; M.legal_mask = G->legal_mask; M.cfg = G->cfg;
     M.obs_dim = G->obs_dim; M.self_obs_dim = G->self_obs_dim;
+    M.sched_T = G->sched_T; M.rowpar = G->rowpar;
+    for (int i = 0; i < SM_MAXSCHED; i++) {
+      for (int k = 0; k < 4; k++) M.sched[i][k] = G->sched[i][k];
+      M.sched_nd[i] = G->sched_nd[i]; M.sched_nc[i] = G->sched_nc[i]; M.sched_ns[i] = G->sched_ns[i];
+    }
   }
   int nb = G->nb, nv = G->nv, ng = G->ng, ns = G->nslot;
   for (int b = tid; b < nb; b += nt) {
@@ -245,6 +251,8 @@ __device__ __noinline__ void w_fk(const WModel<C>& M, float* sm, const WLane& w,
           st6(sm + C::acc + 6 * b, ab);
           float r10[10];
           w_rigid10(M, sm, b, r10);
+#pragma unroll
+          for (int j = 0; j < 10; j++) sm[C::irb + 10 * b + j] = r10[j];
           st6(sm + C::pb + 6 * b, rb_mul(r10, ab) + cross_force(v, rb_mul(r10, v)));
         }
       }
@@ -253,14 +261,187 @@ __device__ __noinline__ void w_fk(const WModel<C>& M, float* sm, const WLane& w,
   }
 }
 
-// ------------------------------------------------------------------ ABA inward sweep
-// flags: 1 INERTIA | 2 FORCE | 4 PB | 8 CONTACTS ; tmode: 0 tau (+limit rows) | 1 zero | 2 stable-PD -kp e - kd qd ; dmode: 0 armature (+limit rows) | 1 + h kd
+// ------------------------------------------------------------------ row-parallel sweeps (LPE == 32): 8 lanes per body, 4 bodies per step
+// Lane r < 6 of an 8-lane group owns row r of the body's 6x6 articulated inertia (and component r of the bias force /
+// acceleration); the 6-vector products become 8-lane shuffle reductions.  Bodies follow the host list schedule
+// M.sched[t][slot] (children strictly before parents, <= 4 bodies per step) instead of the depth levels, so a sweep costs
+// ~T x (a third of the per-body instructions) instead of nlevel x (the slowest body of the level).
+__device__ __forceinline__ float w_sel6(int r, float a0, float a1, float a2, float a3, float a4, float a5) {
+  return r == 0 ? a0 : r == 1 ? a1 : r == 2 ? a2 : r == 3 ? a3 : r == 4 ? a4 : a5;
+}
+__device__ __forceinline__ float w_red8(unsigned gm, float v) {
+  v += __shfl_xor_sync(gm, v, 1);
+  v += __shfl_xor_sync(gm, v, 2);
+  v += __shfl_xor_sync(gm, v, 4);
+  return v;
+}
+
 #define W_INERTIA 1
 #define W_FORCE 2
 #define W_PB 4
 #define W_CONTACTS 8
 template <class C>
+__device__ __noinline__ void w_inward8(const WModel<C>& M, float* sm, const WLane& w, bool run, int flags, int tmode, int dmode) {
+  // fully predicated, warp-uniform control flow: the four 8-lane groups must never diverge from each other, otherwise
+  // the hardware serialises them and the row parallelism is lost
+  const bool inertia = flags & W_INERTIA, force = flags & W_FORCE;
+  const int nlim = (tmode == 0 || dmode == 0) ? ((const int*)sm)[C::lim] : 0;
+  const int slot = w.lane >> 3, r = w.lane & 7, gbase = w.lane & ~7;
+  const bool rowok = r < 6;
+  const int rr = rowok ? r : 5;
+  const int* cflag = (const int*)(sm + C::cflag);
+  int ridx[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) { int i0 = rr < j ? rr : j, j0 = rr < j ? j : rr; ridx[j] = i0 * 6 - (i0 * (i0 - 1)) / 2 + (j0 - i0); }
+  for (int t = 0; t < M.sched_T; t++) {
+    const int b0 = M.sched[t][slot];
+    const bool actv = run && b0 >= 0;
+    const int b = actv ? b0 : 0;
+    const bool rowact = actv && rowok;
+    float Ar[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pr = 0.f;
+    if (inertia && rowact) {
+      const float* q = sm + C::irb + 10 * b;
+      float m = q[0], cx = q[1], cy = q[2], cz = q[3];
+      switch (r) {
+        case 0: Ar[0] = q[4]; Ar[1] = q[7]; Ar[2] = q[8]; Ar[4] = -cz; Ar[5] = cy; break;
+        case 1: Ar[0] = q[7]; Ar[1] = q[5]; Ar[2] = q[9]; Ar[3] = cz; Ar[5] = -cx; break;
+        case 2: Ar[0] = q[8]; Ar[1] = q[9]; Ar[2] = q[6]; Ar[3] = -cy; Ar[4] = cx; break;
+        case 3: Ar[1] = cz; Ar[2] = -cy; Ar[3] = m; break;
+        case 4: Ar[0] = -cz; Ar[2] = cx; Ar[4] = m; break;
+        default: Ar[0] = cy; Ar[1] = -cx; Ar[5] = m; break;
+      }
+    }
+    if (force && (flags & W_PB) && rowact) pr = sm[C::pb + 6 * b + r];
+    if (flags & W_CONTACTS) {
+      const int hasg = (actv && M.bgeom_adr[b + 1] > M.bgeom_adr[b]) ? 1 : 0;
+      const int g = hasg ? M.bgeom_list[M.bgeom_adr[b]] : 0;
+      const int s0 = M.slot_adr[g], nsl = hasg ? M.slot_adr[g + 1] - s0 : 0;
+      const V3 t1 = ld3(sm + C::ct1 + 3 * g);
+      for (int s = 0; s < M.sched_ns[t]; s++) {
+        const int c = s < nsl ? s0 + s : s0;
+        int fl = s < nsl ? cflag[c] : 0;
+        if (!(fl & 1)) fl = 0;
+        if (!__any_sync(W_FULL, (fl & 30) != 0)) continue;
+        const V3 cp = ld3(sm + C::cpos + 3 * c);
+        const float D = sm[C::cD + c];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const bool on = (fl & (2 << k)) != 0;      // select, never multiply: unused slots hold uninitialised shared memory
+          S6 xw = w_wrench(M, cp, t1, k);
+          if (!on) xw = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+          float xr = rowok ? w_sel6(rr, xw.a.x, xw.a.y, xw.a.z, xw.l.x, xw.l.y, xw.l.z) : 0.f;
+          float dx = on ? D * xr : 0.f;
+          if (inertia) {
+            Ar[0] = fmaf(dx, xw.a.x, Ar[0]); Ar[1] = fmaf(dx, xw.a.y, Ar[1]); Ar[2] = fmaf(dx, xw.a.z, Ar[2]);
+            Ar[3] = fmaf(dx, xw.l.x, Ar[3]); Ar[4] = fmaf(dx, xw.l.y, Ar[4]); Ar[5] = fmaf(dx, xw.l.z, Ar[5]);
+          }
+          if (force && on) pr = fmaf(-dx, sm[C::caref + 4 * c + k], pr);
+        }
+      }
+    }
+    {
+      const int ca = M.child_adr[b], ncb = actv ? M.child_adr[b + 1] - ca : 0;
+      for (int ci = 0; ci < M.sched_nc[t]; ci++) {
+        if (ci < ncb && rowok) {
+          int c = M.child_list[ca + ci];
+          if (inertia) {
+#pragma unroll
+            for (int j = 0; j < 6; j++) Ar[j] += sm[C::IA + 21 * c + ridx[j]];
+          }
+          if (force) pr += sm[C::pA + 6 * c + r];
+        }
+      }
+    }
+    const int d0 = M.dofadr[b], ndb = actv ? M.dofnum[b] : 0;
+    for (int k = M.sched_nd[t] - 1; k >= 0; k--) {
+      const bool has = k < ndb;
+      const int d = has ? d0 + k : d0;
+      S6 S = w_dofS(M, sm, b, has ? k : 0);
+      float sr = rowok ? w_sel6(rr, S.a.x, S.a.y, S.a.z, S.l.x, S.l.y, S.l.z) : 0.f;
+      float lD = 0.f, lT = 0.f;
+      for (int e = 0; e < nlim; e++) {
+        if (((const int*)sm)[C::lim + 4 + 8 * e] == d && (((const int*)sm)[C::lim + 4 + 8 * e + 5] & 1)) {
+          lD = WLIM(sm, e, 2); lT = WLIM(sm, e, 1) * lD * WLIM(sm, e, 3);
+        }
+      }
+      float Ur, di;
+      if (inertia) {
+        Ur = Ar[0] * S.a.x;
+        Ur = fmaf(Ar[1], S.a.y, Ur); Ur = fmaf(Ar[2], S.a.z, Ur); Ur = fmaf(Ar[3], S.l.x, Ur); Ur = fmaf(Ar[4], S.l.y, Ur); Ur = fmaf(Ar[5], S.l.z, Ur);
+        float D = w_red8(W_FULL, sr * Ur) + M.arm[d] + ((dmode == 1) ? ((d >= 6) ? M.h * M.kd[d - 6] : 0.f) : lD);
+        di = has ? 1.0f / D : 0.f;
+        float cu = has ? Ur * di : 0.f;
+#pragma unroll
+        for (int j = 0; j < 6; j++) Ar[j] = fmaf(-cu, __shfl_sync(W_FULL, Ur, gbase + j), Ar[j]);
+        if (has && rowok) sm[C::U + 6 * d + r] = Ur;
+        if (has && r == 0) sm[C::Dinv + d] = di;
+      } else {
+        Ur = (has && rowok) ? sm[C::U + 6 * d + r] : 0.f;
+        di = has ? sm[C::Dinv + d] : 0.f;
+      }
+      if (force) {
+        float tin = 0.f;
+        if (d >= 6) {
+          int a = d - 6;
+          if (tmode == 0) tin = sm[C::tau + a] + lT;
+          else if (tmode == 2) {
+            float tgt = fmaf(sm[C::act + a], M.ascale[a], M.aoffset[a]);
+            float err = sm[C::qpos + d + 1] + sm[C::qvel + d] * M.h - tgt;
+            tin = -M.kp[a] * err - M.kd[a] * sm[C::qvel + d];
+          }
+        }
+        float uu = tin - w_red8(W_FULL, sr * pr);
+        if (has && r == 0) sm[C::u + d] = uu;
+        if (has) pr = fmaf(Ur, uu * di, pr);
+      }
+    }
+    if (rowact) {
+      if (inertia) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) if (j >= r) sm[C::IA + 21 * b + ridx[j]] = Ar[j];
+      }
+      if (force) sm[C::pA + 6 * b + r] = pr;
+    }
+    __syncwarp();
+  }
+}
+
+template <class C>
+__device__ __noinline__ void w_outward8(const WModel<C>& M, float* sm, const WLane& w, bool run, int which, int mode) {
+  float* qout = sm + (which == 0 ? C::qacc : which == 1 ? C::qstar : C::spdab);
+  const int slot = w.lane >> 3, r = w.lane & 7;
+  const bool rowok = r < 6;
+  const int rr = rowok ? r : 5;
+  for (int t = M.sched_T - 1; t >= 0; t--) {
+    const int b0 = M.sched[t][slot];
+    const bool actv = run && b0 >= 0;
+    const int b = actv ? b0 : 0;
+    float ar = (b == 0 || !rowok || !actv) ? 0.f : sm[C::acc + 6 * M.parent[b] + r];
+    const int d0 = M.dofadr[b], ndb = actv ? M.dofnum[b] : 0;
+    for (int k = 0; k < M.sched_nd[t]; k++) {
+      const bool has = k < ndb;
+      const int d = has ? d0 + k : d0;
+      S6 S = w_dofS(M, sm, b, has ? k : 0);
+      float sr = rowok ? w_sel6(rr, S.a.x, S.a.y, S.a.z, S.l.x, S.l.y, S.l.z) : 0.f;
+      float qdd;
+      if (mode == 1) qdd = sm[C::qacc + d];
+      else {
+        float Ur = (has && rowok) ? sm[C::U + 6 * d + r] : 0.f;
+        qdd = sm[C::Dinv + d] * (sm[C::u + d] - w_red8(W_FULL, Ur * ar));
+        if (has && r == 0) qout[d] = qdd;
+      }
+      if (has) ar = fmaf(sr, qdd, ar);
+    }
+    if (actv && rowok) sm[C::acc + 6 * b + r] = ar;
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ ABA inward sweep
+// flags: 1 INERTIA | 2 FORCE | 4 PB | 8 CONTACTS ; tmode: 0 tau (+limit rows) | 1 zero | 2 stable-PD -kp e - kd qd ; dmode: 0 armature (+limit rows) | 1 + h kd
+template <class C>
 __device__ __noinline__ void w_inward(const WModel<C>& M, float* sm, const WLane& w, bool run, int flags, int tmode, int dmode) {
+  if (C::LPE == 32 && M.rowpar && M.sched_T > 0) { w_inward8(M, sm, w, run, flags, tmode, dmode); return; }
   const bool inertia = flags & W_INERTIA, force = flags & W_FORCE;
   const int nlim = (tmode == 0 || dmode == 0) ? ((const int*)sm)[C::lim] : 0;
   for (int lev = M.nlevel - 1; lev >= 0; lev--) {
@@ -269,7 +450,7 @@ __device__ __noinline__ void w_inward(const WModel<C>& M, float* sm, const WLane
         int b = M.level_list[i];
         float A[21];
         S6 p = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
-        if (inertia) { float r10[10]; w_rigid10(M, sm, b, r10); rb_expand(r10, A); }
+        if (inertia) rb_expand(sm + C::irb + 10 * b, A);
         if (force && (flags & W_PB)) p = ld6(sm + C::pb + 6 * b);
         if (flags & W_CONTACTS) {
           const int* cflag = (const int*)(sm + C::cflag);
@@ -355,6 +536,7 @@ __device__ __noinline__ void w_inward(const WModel<C>& M, float* sm, const WLane
 // ------------------------------------------------------------------ ABA outward sweep.  which: 0 qacc | 1 qstar | 2 spdab ; mode 1: accumulate S*qacc only
 template <class C>
 __device__ __noinline__ void w_outward(const WModel<C>& M, float* sm, const WLane& w, bool run, int which, int mode) {
+  if (C::LPE == 32 && M.rowpar && M.sched_T > 0) { w_outward8(M, sm, w, run, which, mode); return; }
   float* qout = sm + (which == 0 ? C::qacc : which == 1 ? C::qstar : C::spdab);
   for (int lev = 0; lev < M.nlevel; lev++) {
     if (run) {
