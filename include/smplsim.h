@@ -183,6 +183,13 @@ int smplsim_motion_gather(SmplsimHandle* h, const int32_t* motion_ids_dev, const
                           const int32_t* length_starts_dev, int num_tables, const float* const* tables_dev,
                           const int32_t* widths, float* const* outs_dev, int32_t* frame_idx_dev, void* cuda_stream);
 
+/* estimate_advantages (smpl_sim/learning/learning_utils.py:198-218) on a [T,N] device rollout: reverse scan per env,
+ * delta = r + gamma*V' *not_dead - V ; A = delta + gamma*tau*A' *not_done ; returns = V + A.  next_value (may be NULL = 0)
+ * bootstraps the step after the last one.  Normalisation (mean / unbiased std over the whole, possibly multi-rank, batch) is
+ * left to the caller (smplsim_b200.learning.estimate_advantages). */
+int smplsim_gae(const float* rewards_dev, const float* not_done_dev, const float* not_dead_dev, const float* values_dev,
+                const float* next_value_dev, float gamma, float tau, int T, int N, float* adv_dev, float* ret_dev, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

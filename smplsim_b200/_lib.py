@@ -44,6 +44,8 @@ _SYMBOLS = {
     "smplsim_self_obs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "smplsim_motion_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "smplsim_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p,
+                              C.c_void_p, C.c_void_p]),
     "smplsim_smem_bytes_per_env": (C.c_int, [C.c_void_p]),
     "smplsim_warps_per_block": (C.c_int, [C.c_void_p]),
     "smplsim_kernel_version": (C.c_int, [C.c_void_p]),

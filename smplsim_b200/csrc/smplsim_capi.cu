@@ -450,3 +450,32 @@ extern "C" int smplsim_motion_gather(SmplsimHandle* h, const int32_t* motion_ids
   CUDA_TRY(cudaGetLastError());
   return SMPLSIM_OK;
 }
+
+// ------------------------------------------------------------------ GAE: learning_utils.estimate_advantages:198-218 as a reverse scan
+// per env column of the [T,N] rollout; thread per env, coalesced across envs at every t.
+__global__ void k_gae(const float* __restrict__ rew, const float* __restrict__ not_done, const float* __restrict__ not_dead,
+                      const float* __restrict__ val, const float* __restrict__ next_val, float gamma, float tau, int T, int N,
+                      float* __restrict__ adv, float* __restrict__ ret) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  float prev_v = next_val ? next_val[e] : 0.f, prev_a = 0.f;
+  for (int t = T - 1; t >= 0; t--) {
+    size_t i = (size_t)t * N + e;
+    float v = val[i];
+    float delta = rew[i] + gamma * prev_v * not_dead[i] - v;
+    float a = delta + gamma * tau * prev_a * not_done[i];
+    adv[i] = a;
+    ret[i] = v + a;
+    prev_v = v; prev_a = a;
+  }
+}
+
+extern "C" int smplsim_gae(const float* rewards_dev, const float* not_done_dev, const float* not_dead_dev, const float* values_dev,
+                           const float* next_value_dev, float gamma, float tau, int T, int N, float* adv_dev, float* ret_dev, void* stream) {
+  if (!rewards_dev || !not_done_dev || !not_dead_dev || !values_dev || !adv_dev || !ret_dev || T < 0 || N < 0)
+    return fail(SMPLSIM_EINVAL, "smplsim_gae: null argument");
+  if (T == 0 || N == 0) return SMPLSIM_OK;
+  k_gae<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards_dev, not_done_dev, not_dead_dev, values_dev, next_value_dev, gamma, tau, T, N, adv_dev, ret_dev);
+  CUDA_TRY(cudaGetLastError());
+  return SMPLSIM_OK;
+}

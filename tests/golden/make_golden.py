@@ -255,7 +255,26 @@ def gen_frame_blend(seed=3, B=256):
     print("frame_blend.npz:", frame_idx[:8])
 
 
+def gen_gae(seed=5, T=24, N=6):
+    """estimate_advantages (smpl_sim/learning/learning_utils.py:198-218) on N concatenated env columns of length T; every column
+    ends with not_done = 0 (as every sampled trajectory does in Agent.sample_worker), so the flat recursion restarts per column."""
+    import torch
+    LU = _import_with_stubs(lambda: __import__("smpl_sim.learning.learning_utils", fromlist=["x"]))
+    rng = np.random.default_rng(seed)
+    rew = rng.uniform(0, 1, (T, N)).astype(np.float32)
+    val = rng.normal(size=(T, N)).astype(np.float32)
+    not_dead = (rng.random((T, N)) > 0.06).astype(np.float32)
+    not_done = not_dead * (rng.random((T, N)) > 0.05).astype(np.float32)
+    not_done[-1] = 0
+    flat = lambda a: torch.from_numpy(np.ascontiguousarray(a.T).reshape(-1, 1).copy())       # env-major concatenation
+    adv, ret = LU.estimate_advantages(flat(rew), flat(not_done), flat(not_dead), flat(val), 0.99, 0.95)
+    np.savez_compressed(os.path.join(HERE, "gae.npz"), rewards=rew, values=val, not_dead=not_dead, not_done=not_done,
+                        advantages=adv.numpy().reshape(N, T).T, returns=ret.numpy().reshape(N, T).T)
+    print("gae.npz:", adv.shape, float(adv.mean()), float(adv.std()))
+
+
 if __name__ == "__main__":
+    gen_gae()
     gen_obs("smpl", 24, 69, seed=11)
     gen_obs("smplx", 52, 153, seed=12, B=8)
     gen_controllers()

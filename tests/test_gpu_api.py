@@ -123,3 +123,35 @@ def test_smplx_env_step_matches_oracle():
         assert np.abs(o0 - obs0[i]).max() < 5e-3
         o, r, te, tr = e.step(act[i])
         assert np.abs(o - obs[i]).max() < 1e-2 and abs(r - rew[i]) < 1e-3
+
+
+def test_gae_matches_reference_golden():
+    """estimate_advantages CUDA reverse scan vs the reference's Python loop (tests/golden/gae.npz)."""
+    from smplsim_b200.learning import estimate_advantages
+    g = np.load(os.path.join(GOLDEN, "gae.npz"))
+    t = lambda k: torch.as_tensor(g[k], dtype=torch.float32, device="cuda:0")  # noqa: E731
+    # the reference scans ONE flat batch: the last sample of a column that is truncated but not dead bootstraps from the next
+    # stored sample, i.e. the first value of the following column (0 after the very last one)
+    nxt = torch.cat([t("values")[0, 1:], torch.zeros(1, device="cuda:0")])
+    adv, ret = estimate_advantages(t("rewards"), t("not_done"), t("not_dead"), t("values"), 0.99, 0.95, next_value=nxt)
+    assert np.abs(adv.cpu().numpy() - g["advantages"]).max() < 2e-5
+    assert np.abs(ret.cpu().numpy() - g["returns"]).max() < 2e-5
+
+
+def test_batched_sampler_shapes_and_masks():
+    from smplsim_b200.batched import HumanoidBatchB200
+    from smplsim_b200.learning import BatchedSampler, estimate_advantages
+    cfg = make_cfg(env="speed", overrides={"env.episode_length": 5})
+    n, T = 64, 8
+    env = HumanoidBatchB200(cfg, num_envs=n, seed=3)
+    torch.manual_seed(0)
+    W = torch.randn(env.num_obs, env.num_actions, device="cuda:0") * 0.01
+    sampler = BatchedSampler(env, lambda o: o @ W)
+    b = sampler.sample(T)
+    assert b["states"].shape == (T, n, 292) and b["actions"].shape == (T, n, 69) and b["rewards"].shape == (T, n)
+    assert b["states"].abs().max() <= 5.0 and b["actions"].abs().max() <= 1.0
+    nd = b["not_done"].cpu().numpy()
+    assert (nd[5] == 0).all() and (nd[:5] == 1).all()            # cur_t = 6 > 5 at the 6th step: every env truncates together
+    assert torch.equal(b["states"][6, :, 0], torch.full((n,), 0.94, device="cuda:0"))   # next state after the in-stream reset
+    adv, ret = estimate_advantages(b["rewards"], b["not_done"], b["not_dead"], torch.zeros(T, n, device="cuda:0"), 0.99, 0.95)
+    assert torch.isfinite(adv).all() and abs(adv.mean().item()) < 1e-4 and abs(adv.std().item() - 1) < 1e-3
