@@ -15,8 +15,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 def sources():
-    return [os.path.join(_CSRC, f) for f in ("smplsim_capi.cu", "env_kernels.cuh", "physics.cuh", "dev_model.cuh", "chain_kernels.cuh", "chain_model.cuh",
-                                                    "chain_host.hpp")] + [
+    import glob
+    return sorted(glob.glob(os.path.join(_CSRC, "*.cu")) + glob.glob(os.path.join(_CSRC, "*.cuh")) + glob.glob(os.path.join(_CSRC, "*.hpp"))) + [
         os.path.join(_HERE, "..", "include", "smplsim.h")]
 
 

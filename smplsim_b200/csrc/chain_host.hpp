@@ -15,12 +15,13 @@ struct ChainPlan {
   std::vector<ChainEntry> tab;   // [T][CH_LPE]
 };
 
-static ChainPlan chain_plan(const SmplsimModelDesc* s, int max_ledge) {
+static ChainPlan chain_plan(const SmplsimModelDesc* s, int max_ledge, bool split_root = true) {
   ChainPlan P;
-  const int nb = s->nbody, npb = nb + 1;
+  const int nb = s->nbody, off = split_root ? 1 : 0, npb = nb + off;
   std::vector<int> par(npb), depth(npb, 0);
-  par[0] = -1; par[1] = 0; depth[1] = 1;
-  for (int b = 1; b < nb; b++) { par[b + 1] = s->body_parent[b] + 1; depth[b + 1] = depth[par[b + 1]] + 1; }
+  par[0] = -1;
+  if (split_root) { par[1] = 0; depth[1] = 1; }
+  for (int b = 1; b < nb; b++) { par[b + off] = s->body_parent[b] + off; depth[b + off] = depth[par[b + off]] + 1; }
   std::vector<std::vector<int>> kids(npb);
   for (int p = 1; p < npb; p++) kids[par[p]].push_back(p);
   // one geom per body
@@ -74,6 +75,11 @@ static ChainPlan chain_plan(const SmplsimModelDesc* s, int max_ledge) {
     if (lane[p] == lane[q]) {
       par_t[p] = step[q];
       if (step[q] == step[p] + 1 && !carry_in[q]) { carry_out[p] = 1; carry_in[q] = 1; continue; }
+      if (!split_root) {   // thread-per-env kernels: every non-carried edge is a shared-memory stash slot
+        int id = CH_EDGE_MBOX + P.n_xedge++;
+        out_edge[p] = id; in_edges[q].push_back(id);
+        continue;
+      }
       int id = nle[lane[p]]++;
       out_edge[p] = id; in_edges[q].push_back(id);
     } else {
@@ -92,26 +98,35 @@ static ChainPlan chain_plan(const SmplsimModelDesc* s, int max_ledge) {
   for (int p = 0; p < npb; p++) {
     ChainEntry& e = P.tab[(size_t)step[p] * CH_LPE + lane[p]];
     e.pb = p;
-    e.kind = p == 0 ? CH_KIND_ROOTTRANS : p == 1 ? CH_KIND_ROOTROT : CH_KIND_HINGE;
-    int b = p == 0 ? 0 : p - 1;
+    int b;
+    if (split_root) {
+      e.kind = p == 0 ? CH_KIND_ROOTTRANS : p == 1 ? CH_KIND_ROOTROT : CH_KIND_HINGE;
+      b = p == 0 ? 0 : p - 1;
+      e.ndof = p <= 1 ? 3 : s->body_dofnum[b];
+      e.dofadr = p == 0 ? 0 : p == 1 ? 3 : s->body_dofadr[b];
+    } else {
+      e.kind = p == 0 ? CH_KIND_ROOT6 : CH_KIND_HINGE;
+      b = p;
+      e.ndof = s->body_dofnum[b];
+      e.dofadr = s->body_dofadr[b];
+    }
     e.body = b;
-    e.ndof = p <= 1 ? 3 : s->body_dofnum[b];
-    e.dofadr = p == 0 ? 0 : p == 1 ? 3 : s->body_dofadr[b];
+    e.par_body = b == 0 ? -1 : s->body_parent[b];
     e.par_t = par_t[p]; e.par_mbox = par_mbox[p]; e.out_mbox = out_mbox[p];
     e.carry_in = carry_in[p]; e.carry_out = carry_out[p]; e.out_edge = out_edge[p];
     for (size_t i = 0; i < in_edges[p].size(); i++) e.in_edge[i] = in_edges[p][i];
-    if (p == 0) continue;
+    if (p == 0 && split_root) continue;
     for (int k = 0; k < 3; k++) { e.bpos[k] = (float)s->body_pos[3 * b + k]; e.ipos[k] = (float)s->body_ipos[3 * b + k]; }
     for (int k = 0; k < 4; k++) e.bquat[k] = (float)s->body_quat[4 * b + k];
     for (int k = 0; k < 6; k++) e.inertia[k] = (float)s->body_inertia[6 * b + k];
     e.mass = (float)s->body_mass[b];
     e.tran_iw0 = (float)s->body_invweight0[2 * b];
-    for (int k = 0; k < e.ndof; k++) {
+    for (int k = 0; k < e.ndof && k < 3 && e.kind != CH_KIND_ROOT6; k++) {
       int d = e.dofadr + k;
       for (int j = 0; j < 3; j++) e.axis[3 * k + j] = (float)s->dof_axis[3 * d + j];
       e.arm[k] = (float)s->dof_armature[d]; e.diw0[k] = (float)s->dof_invweight0[d];
       e.range[2 * k] = (float)s->dof_range[2 * d]; e.range[2 * k + 1] = (float)s->dof_range[2 * d + 1];
-      if (p > 1) {
+      if (e.kind == CH_KIND_HINGE) {
         if (s->dof_limited[d]) e.limited |= 1 << k;
         int i = d - 6;
         e.kp[k] = (float)s->act_kp[i]; e.kd[k] = (float)s->act_kd[i]; e.tlim[k] = (float)s->act_torque_lim[i];

@@ -19,6 +19,7 @@
 #define CH_KIND_HINGE 0
 #define CH_KIND_ROOTROT 1
 #define CH_KIND_ROOTTRANS 2
+#define CH_KIND_ROOT6 3      // un-split free-joint root (6 dofs) -- thread-per-env kernels
 
 struct ChainEntry {       // one (step, lane) cell; 4-byte words only (staged into shared memory as-is)
   int pb;                 // pseudo-body id, -1 = idle
@@ -32,11 +33,11 @@ struct ChainEntry {       // one (step, lane) cell; 4-byte words only (staged in
   int out_edge;           // where Ia/pa go when not carried (-1: carried or tree root)
   int geom, gtype;        // MuJoCo-order geom index (robot geoms, 0-based) or -1
   int limited;            // bit k: dof k is range-limited
+  int par_body;           // MuJoCo-order parent body (-1: tree root)
   float bpos[3], bquat[4], mass, ipos[3], inertia[6], tran_iw0;
   float axis[9], arm[3], diw0[3], range[6];
   float kp[3], kd[3], tlim[3], ascale[3], aoffset[3];
   float gpos[3], gmat[9], gsize[3];
-  int pad;                // keeps the stride odd (bank spread across the 4 lanes)
 };
 
 struct ChainConsts {      // scalars, passed by value (constant bank)

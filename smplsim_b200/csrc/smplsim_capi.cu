@@ -10,6 +10,7 @@
 #include "chain_kernels.cuh"
 #include "chain_host.hpp"
 #include "warp_kernels.cuh"
+#include "tpe_kernels.cuh"
 #include <cstdlib>
 #include <algorithm>
 
@@ -29,7 +30,22 @@ struct SmplsimHandle {
   // v3 (level-synchronous, compile-time layout): cls 0 none, 1 SMPL lpe32, 2 SMPL lpe16, 3 SMPL-X, 4 generic
   int v3cls = 0, wpb3 = 4, align3 = 1;
   size_t smem3 = 0;
+  // v4 (thread-per-env x chain-per-warp)
+  bool v4 = false;
+  TpeTable* tab4 = nullptr;     // host copy, uploaded to __constant__ c_tpe when this handle becomes the active one
+  float* gs4 = nullptr;
+  size_t npad4 = 0, smem4 = 0;
+  std::string v4_why;
 };
+
+typedef TCfg<24, 75, 12> TC_SMPL;
+static const SmplsimHandle* g_tpe_owner = nullptr;
+static int tpe_activate(SmplsimHandle* h, cudaStream_t st) {
+  if (g_tpe_owner == h) return 0;
+  if (cudaMemcpyToSymbolAsync(c_tpe, h->tab4, sizeof(TpeTable), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+  g_tpe_owner = h;
+  return 0;
+}
 
 typedef WCfg<24, 75, 24, 64, 32> WC_SMPL32;
 typedef WCfg<24, 75, 24, 64, 16> WC_SMPL16;
@@ -238,6 +254,8 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
       }
       m.sched_nd[tt] = nd; m.sched_nc[tt] = nc; m.sched_ns[tt] = ns;
     }
+    const char* ws = std::getenv("SMPLSIM_WARMSET");
+    m.warmset = ws ? std::atoi(ws) : 1;
     const char* rp = std::getenv("SMPLSIM_ROWS");
     m.rowpar = rp ? std::atoi(rp) : 0;   // opt-in: measured slower than the level sweeps in round 1 (profiles/r1_k_step3_rows.md)
   }
@@ -288,6 +306,39 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
       h->v2 = true;
     }
   }
+  // ---- v4: thread-per-env x chain-per-warp (SMPL-sized models)
+  {
+    const char* force = std::getenv("SMPLSIM_KERNEL");
+    bool want = force ? std::string(force) == "v4" : false;
+    ChainPlan P = chain_plan(s, 0, false);
+    if (!want) h->v4_why = "not selected";
+    else if (h->v2) h->v4_why = "v2 forced";
+    else if (!P.ok) h->v4_why = P.why;
+    else if (P.T > TPE_MAXT) h->v4_why = "schedule longer than 16 steps";
+    else if (m.nb != TC_SMPL::NB || m.nv != TC_SMPL::NV) h->v4_why = "model size is not the SMPL class (24 bodies, 75 dofs)";
+    else if (P.n_xedge > TC_SMPL::NE) h->v4_why = "too many junction edges";
+    else {
+      h->tab4 = new TpeTable();
+      std::memset(h->tab4, 0, sizeof(TpeTable));
+      ChainConsts& k = h->tab4->K;
+      k.T = P.T; k.nb = m.nb; k.nq = m.nq; k.nv = m.nv; k.nu = m.nu; k.ng = m.ng; k.n_mbox = 0; k.n_xedge = P.n_xedge; k.mb_stride = 0;
+      k.obs_dim = m.obs_dim; k.self_obs_dim = m.self_obs_dim;
+      for (int i = 0; i < 3; i++) { k.plane_pos[i] = m.plane_pos[i]; k.plane_n[i] = m.plane_n[i]; k.t1_default[i] = m.t1_default[i]; k.grav[i] = m.grav[i]; }
+      k.margin = m.margin; k.mu = m.mu; k.impratio = m.impratio;
+      for (int i = 0; i < 5; i++) k.solimp[i] = m.solimp[i];
+      k.imp_a = m.imp_a; k.imp_b = m.imp_b; k.K = m.K; k.B = m.B; k.h = m.h; k.legal_mask = m.legal_mask; k.cfg = m.cfg;
+      for (int t = 0; t < P.T; t++) for (int w = 0; w < TPE_WARPS; w++) h->tab4->e[t][w] = P.tab[(size_t)t * CH_LPE + w];
+      for (int t = P.T; t < TPE_MAXT; t++) for (int w = 0; w < TPE_WARPS; w++) h->tab4->e[t][w].pb = -1;
+      h->npad4 = ((size_t)num_envs + 31) & ~(size_t)31;
+      h->smem4 = (size_t)TC_SMPL::smem_words * 32 * 4;
+      cudaError_t e4 = cudaMalloc(&h->gs4, (size_t)TC_SMPL::g_words * h->npad4 * 4);
+      if (e4 == cudaSuccess) e4 = cudaMemset(h->gs4, 0, (size_t)TC_SMPL::g_words * h->npad4 * 4);
+      if (e4 == cudaSuccess) e4 = cudaFuncSetAttribute(k_step4<TC_SMPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem4);
+      if (e4 == cudaSuccess) e4 = cudaFuncSetAttribute(k_reset4<TC_SMPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem4);
+      if (e4 != cudaSuccess) { h->v4_why = std::string("cuda: ") + cudaGetErrorString(e4); cudaGetLastError(); if (h->gs4) cudaFree(h->gs4); h->gs4 = nullptr; delete h->tab4; h->tab4 = nullptr; }
+      else h->v4 = true;
+    }
+  }
   // ---- v3: default hot path
   {
     const char* force = std::getenv("SMPLSIM_KERNEL");
@@ -296,8 +347,8 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
     if (al) h->align3 = std::atoi(al);
     const char* wp = std::getenv("SMPLSIM_WPB");
     h->wpb3 = wp ? std::atoi(wp) : 0;
-    bool want = !force || std::string(force) == "v3";
-    if (want && !h->v2) {
+    bool want = !force || std::string(force) == "v3" || std::string(force) == "v4";
+    if (want && !h->v2 && !h->v4) {
       int cls;
       if (m.nb <= 24 && m.nv <= 75 && m.ng <= 24 && m.nslot <= 64) cls = (lpe && std::string(lpe) == "16") ? 2 : (lpe && std::string(lpe) == "8") ? 5 : 1;
       else if (m.nb <= 52 && m.nv <= 159 && m.ng <= 52 && m.nslot <= 120) cls = 3;
@@ -316,6 +367,9 @@ extern "C" int smplsim_destroy(SmplsimHandle* h) {
   cudaSetDevice(h->device);
   cudaFree(h->dm);
   if (h->d_tab) cudaFree(h->d_tab);
+  if (h->gs4) cudaFree(h->gs4);
+  if (g_tpe_owner == h) g_tpe_owner = nullptr;
+  delete h->tab4;
   delete h;
   return SMPLSIM_OK;
 }
@@ -328,7 +382,7 @@ extern "C" int smplsim_smem_bytes_per_env(const SmplsimHandle* h) {
 }
 extern "C" int smplsim_warps_per_block(const SmplsimHandle* h) { return h ? (h->v3cls ? h->wpb3 : h->v2 ? h->wpb2 : h->wpb) : SMPLSIM_EINVAL; }
 /* 2: chain-lane kernels (4 lanes/env), 1: generic warp-per-env kernels; steps of the chain schedule */
-extern "C" int smplsim_kernel_version(const SmplsimHandle* h) { return h ? (h->v2 ? 2 : h->v3cls ? 3 : 1) : SMPLSIM_EINVAL; }
+extern "C" int smplsim_kernel_version(const SmplsimHandle* h) { return h ? (h->v4 ? 4 : h->v2 ? 2 : h->v3cls ? 3 : 1) : SMPLSIM_EINVAL; }
 extern "C" int smplsim_schedule_steps(const SmplsimHandle* h) { return h ? (h->v2 ? h->kc.T : h->hm.nlevel) : SMPLSIM_EINVAL; }
 
 static dim3 grid2(const SmplsimHandle* h, int n) { int per = h->wpb2 * CH_EPW; return dim3((n + per - 1) / per); }
@@ -354,7 +408,12 @@ extern "C" int smplsim_step(SmplsimHandle* h, const SmplsimState* st, const floa
   a.st = *st; if (aux) a.aux = *aux;
   a.action = action_dev; a.obs = obs_dev; a.reward = reward_dev; a.terminated = terminated_dev; a.truncated = truncated_dev;
   a.n = h->num_envs; a.nsub = h->hm.cfg.nsubsteps; a.mode = 0;
-  if (h->v3cls) {
+  if (h->v4) {
+    if (tpe_activate(h, (cudaStream_t)stream)) return fail(SMPLSIM_ECUDA, "constant table upload failed");
+    TpeStepArgs b; b.st = a.st; b.aux = a.aux; b.action = a.action; b.obs = a.obs; b.reward = a.reward; b.terminated = a.terminated;
+    b.truncated = a.truncated; b.gs = h->gs4; b.npad = h->npad4; b.n = a.n; b.nsub = a.nsub; b.mode = 0;
+    k_step4<TC_SMPL><<<(a.n + 31) / 32, 128, h->smem4, (cudaStream_t)stream>>>(b);
+  } else if (h->v3cls) {
     WStepArgs b; b.st = a.st; b.aux = a.aux; b.action = a.action; b.obs = a.obs; b.reward = a.reward; b.terminated = a.terminated;
     b.truncated = a.truncated; b.n = a.n; b.nsub = a.nsub; b.mode = 0; b.align = h->align3;
     launch_step3(h, b, (cudaStream_t)stream);
@@ -373,7 +432,12 @@ extern "C" int smplsim_mj_step(SmplsimHandle* h, const SmplsimState* st, const f
   StepArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
   a.action = ctrl_dev; a.n = h->num_envs; a.nsub = nsub; a.mode = 1;
-  if (h->v3cls) {
+  if (h->v4) {
+    if (tpe_activate(h, (cudaStream_t)stream)) return fail(SMPLSIM_ECUDA, "constant table upload failed");
+    TpeStepArgs b; std::memset(&b, 0, sizeof b);
+    b.st = a.st; b.aux = a.aux; b.action = a.action; b.gs = h->gs4; b.npad = h->npad4; b.n = a.n; b.nsub = a.nsub; b.mode = 1;
+    k_step4<TC_SMPL><<<(a.n + 31) / 32, 128, h->smem4, (cudaStream_t)stream>>>(b);
+  } else if (h->v3cls) {
     WStepArgs b; std::memset(&b, 0, sizeof b);
     b.st = a.st; b.aux = a.aux; b.action = a.action; b.n = a.n; b.nsub = a.nsub; b.mode = 1; b.align = h->align3;
     launch_step3(h, b, (cudaStream_t)stream);
@@ -396,7 +460,12 @@ extern "C" int smplsim_reset(SmplsimHandle* h, const SmplsimState* st, const uin
   ResetArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
   a.mask = mask_dev; a.qpos0 = qpos0_dev; a.qvel0 = qvel0_dev; a.obs = obs_dev; a.n = h->num_envs; a.init_mode = mode;
-  if (h->v3cls) {
+  if (h->v4) {
+    if (tpe_activate(h, (cudaStream_t)stream)) return fail(SMPLSIM_ECUDA, "constant table upload failed");
+    TpeResetArgs b; b.st = a.st; b.aux = a.aux; b.mask = a.mask; b.qpos0 = a.qpos0; b.qvel0 = a.qvel0; b.obs = a.obs; b.gs = h->gs4; b.npad = h->npad4;
+    b.n = a.n; b.init_mode = a.init_mode;
+    k_reset4<TC_SMPL><<<(a.n + 31) / 32, 128, h->smem4, (cudaStream_t)stream>>>(b);
+  } else if (h->v3cls) {
     WResetArgs b; b.st = a.st; b.aux = a.aux; b.mask = a.mask; b.qpos0 = a.qpos0; b.qvel0 = a.qvel0; b.obs = a.obs; b.n = a.n; b.init_mode = a.init_mode;
     launch_reset3(h, b, (cudaStream_t)stream);
   } else if (h->v2) {

@@ -40,7 +40,7 @@ struct WCfg {
 // constants staged per CTA (float32 image of the model, exact sizes)
 template <class C>
 struct WModel {
-  int nb, nv, nu, ng, nlevel, nslot, sched_T, rowpar;
+  int nb, nv, nu, ng, nlevel, nslot, sched_T, rowpar, warmset;
   int sched[SM_MAXSCHED][4], sched_nd[SM_MAXSCHED], sched_nc[SM_MAXSCHED], sched_ns[SM_MAXSCHED];
   int parent[C::NB], dofadr[C::NB], dofnum[C::NB];
   int level_adr[SM_MAXL + 1], level_list[C::NB], child_adr[C::NB + 1], child_list[C::NB];
@@ -66,7 +66,7 @@ __device__ void w_stage_model(const DevModel* __restrict__ G, WModel<C>& M) {
     for (int i = 0; i < 5; i++) M.solimp[i] = G->solimp[i];
     M.imp_a = G->imp_a; M.imp_b = G->imp_b; M.K = G->K; M.B = G->B; M.h = G->h; M.legal_mask = G->legal_mask; M.cfg = G->cfg;
     M.obs_dim = G->obs_dim; M.self_obs_dim = G->self_obs_dim;
-    M.sched_T = G->sched_T; M.rowpar = G->rowpar;
+    M.sched_T = G->sched_T; M.rowpar = G->rowpar; M.warmset = G->warmset;
     for (int i = 0; i < SM_MAXSCHED; i++) {
       for (int k = 0; k < 4; k++) M.sched[i][k] = G->sched[i][k];
       M.sched_nd[i] = G->sched_nd[i]; M.sched_nc[i] = G->sched_nc[i]; M.sched_ns[i] = G->sched_ns[i];
@@ -580,7 +580,8 @@ __device__ __noinline__ unsigned long long w_collide(const WModel<C>& M, float* 
       V3 c = ld3(sm + C::xpos + 3 * b) + mrot(R, ld3(M.gpos[g]));
       float d0 = h0 + dot(n, c);
       int s0 = M.slot_adr[g], s1 = M.slot_adr[g + 1], cnt = 0;
-      for (int s = s0; s < s1; s++) cflag[s] = 0;
+      int prevfl[4] = {0, 0, 0, 0};
+      for (int s = s0; s < s1; s++) { if (s - s0 < 4) prevfl[s - s0] = cflag[s]; cflag[s] = 0; }
       const float* gm = M.gmat[g];
       int ty = M.gtype[g];
       V3 t1 = ld3(M.t1_default);
@@ -622,7 +623,8 @@ __device__ __noinline__ unsigned long long w_collide(const WModel<C>& M, float* 
           sm[C::cD + c2] = 1.0f / (2.f * mu * mu * R0);
           float kterm = M.K * imp * pm;
           for (int k = 0; k < 4; k++) sm[C::caref + 4 * c2 + k] = -M.B * dot6(w_wrench(M, cp_s[s], t1, k), v) - kterm;
-          cflag[c2] = 1;
+          // warmset: start from the working set this slot ended the previous substep with (new contacts: all rows active)
+          cflag[c2] = M.warmset ? (1 | ((prevfl[s] & 1) ? (prevfl[s] & 30) : 30)) : 1;
         }
         mask |= 1ull << (g + 1);
         nrows += 4 * cnt;
@@ -643,7 +645,7 @@ __device__ __noinline__ unsigned long long w_collide(const WModel<C>& M, float* 
         WLIM(sm, e, 2) = 1.0f / fmaxf((1.f - imp) / imp * M.diw0[d], 1e-15f);
         WLIM(sm, e, 3) = -M.B * sg * sm[C::qvel + d] - M.K * imp * dist;
         WLIM(sm, e, 4) = 0.f;
-        lim[4 + 8 * e + 5] = 0;
+        lim[4 + 8 * e + 5] = M.warmset ? 1 : 0;
         nrows++;
       }
     }
@@ -748,8 +750,10 @@ __device__ __noinline__ int w_solve(const WModel<C>& M, float* sm, const WLane& 
   }
   bool run = w.live && any_rows;
   if (!__any_sync(W_FULL, run)) return 0;
-  w_outward(M, sm, w, run, 0, 1);
-  w_eval_rows(M, sm, w, run, 0);
+  if (!M.warmset) {            // initial working set from the previous qacc (MuJoCo-style warm start) ...
+    w_outward(M, sm, w, run, 0, 1);
+    w_eval_rows(M, sm, w, run, 0);
+  }                            // ... or inherited per contact slot from the previous substep (set in w_collide)
   bool have_point = false;
   int it = 0, iters = 0;
   float o4[4];
@@ -1076,6 +1080,7 @@ __global__ void __launch_bounds__(512) k_step3(const DevModel* __restrict__ G, W
   size_t eo = w.live ? (size_t)env : 0;   // warps without a live env keep running (predicated) so CTA barriers stay legal
   const bool spd = (M.cfg.control_mode == SMPLSIM_CTRL_UHC_PD);
   if (w.live && w.li == 0) ((int*)sm)[C::lim] = 0;
+  if (w.live) for (int c = w.li; c < M.nslot; c += C::LPE) ((int*)sm)[C::cflag + c] = 0;   // no inherited working set at launch
   if (spd && M.cfg.spd_stale && a.mode == 0) {   // factors of (M + h Kd) at the state of the last forward pass (quirk Q1)
     w_copy<C>(sm + C::qpos, a.st.qpos_fwd + eo * (M.nv + 1), M.nv + 1, w);
     w_copy<C>(sm + C::qvel, a.st.qvel_fwd + eo * M.nv, M.nv, w);
@@ -1144,6 +1149,7 @@ __global__ void __launch_bounds__(512) k_reset3(const DevModel* __restrict__ G, 
   if (w.live && w.li == 0) {
     int* ti = (int*)(sm + C::tsk);
     ((int*)sm)[C::lim] = 0;
+    for (int c = 0; c < M.nslot; c++) ((int*)sm)[C::cflag + c] = 0;
     if (c.task == SMPLSIM_TASK_GETUP) ti[W_TSK_RECOV] = c.recovery_steps;
     if (!c.legacy_change_step) ti[W_TSK_CURT] = 0;
     w_reset_task(M, sm, env);   // sees the old cur_t when legacy_change_step (quirk Q4)

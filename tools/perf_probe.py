@@ -22,4 +22,9 @@ torch.cuda.synchronize(); t0 = time.time()
 for i in range(8):
     env.step(acts[warm + i]); env.reset_done()
 torch.cuda.synchronize(); dt = (time.time() - t0) / 8
-print(f"kernel v{env.kernel_version} N={n}: {dt * 1e3:.3f} ms/step -> {n / dt / 1e6:.3f} M env-steps/s")
+env2 = HumanoidBatchB200(make_cfg(env="speed"), num_envs=min(n, 1024))
+env2.reset()
+its = []
+for i in range(warm + 8):
+    env2.step(acts[i][: env2.num_envs]); its.append(env2.solver_iter.float().mean().item()); env2.reset_done()
+print(f"kernel v{env.kernel_version} N={n}: {dt * 1e3:.3f} ms/step -> {n / dt / 1e6:.3f} M env-steps/s ; mean extra solves (last substep) {sum(its[-8:]) / 8:.2f}")
