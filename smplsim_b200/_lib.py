@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsmplsim_b200.so")
+SO_PATH = os.environ.get("SMPLSIM_SO") or os.path.join(_HERE, "libsmplsim_b200.so")   # SMPLSIM_SO: debug builds (tools/)
 _CSRC = os.path.join(_HERE, "csrc")
 _LIB = None
 

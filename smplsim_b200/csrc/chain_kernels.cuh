@@ -618,7 +618,7 @@ __device__ __noinline__ int ch_solve(const ChainConsts& K, const ChainCtx& x, Ch
       ch_ls(K, x, L, lsrch, 0.f, &s1, &s2);
       s1 = ch_envsum(s1);
       float f0 = g1 + s1, al = 0.f, lo = 0.f, hi = -1.f, tol = 1e-6f * fabsf(f0);
-      bool searching = lsrch && (f0 < 0.f);
+      bool searching = lsrch && (f0 < -1e-4f * (fabsf(g1) + fabsf(s1)));
       if (searching) al = 1.f;
       for (int ls = 0; ls < CH_LS_MAXITER; ls++) {
         if (!__any_sync(CH_FULL, searching)) break;
@@ -631,6 +631,7 @@ __device__ __noinline__ int ch_solve(const ChainConsts& K, const ChainCtx& x, Ch
             if (f < 0.f) lo = al; else hi = al;
             float an = (fp > 0.f) ? al - f / fp : -1.f;
             if (!(an > lo) || (hi > 0.f && !(an < hi))) an = (hi > 0.f) ? 0.5f * (lo + hi) : 2.f * al;
+            an = fminf(an, 16.f);
             if (an == al) searching = false; else al = an;
           }
         }

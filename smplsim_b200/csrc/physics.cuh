@@ -513,7 +513,7 @@ __device__ int solve_constrained(const DevModel& M, const EnvLayout& L, float* s
     ls_sums(M, L, sm, lane, 0.f, s1, s2);
     s1 = warp_sum(s1); s2 = warp_sum(s2);
     float f0 = g1 + s1, al = 0.f;
-    if (f0 < 0.f) {
+    if (f0 < -1e-4f * (fabsf(g1) + fabsf(s1))) {   // below the fp32 cancellation floor: converged
       float lo = 0.f, hi = -1.f, tol = 1e-6f * fabsf(f0);
       al = 1.f;
       for (int ls = 0; ls < LS_MAXITER; ls++) {
@@ -524,6 +524,7 @@ __device__ int solve_constrained(const DevModel& M, const EnvLayout& L, float* s
         if (f < 0.f) lo = al; else hi = al;
         float an = (fp > 0.f) ? al - f / fp : -1.f;
         if (!(an > lo) || (hi > 0.f && !(an < hi))) an = (hi > 0.f) ? 0.5f * (lo + hi) : 2.f * al;
+        an = fminf(an, 16.f);
         if (an == al) break;
         al = an;
       }

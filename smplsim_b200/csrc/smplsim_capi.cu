@@ -548,3 +548,17 @@ extern "C" int smplsim_gae(const float* rewards_dev, const float* not_done_dev, 
   CUDA_TRY(cudaGetLastError());
   return SMPLSIM_OK;
 }
+
+#ifdef SMPLSIM_TRACE
+extern "C" int smplsim_debug_trace(float* out, int maxn) {
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(int));
+  if (n > 8192) n = 8192;
+  if (n > maxn) n = maxn;
+  cudaMemcpyFromSymbol(out, g_trace, sizeof(float) * n);
+  int z = 0;
+  cudaMemcpyToSymbol(g_trace_n, &z, sizeof(int));
+  return n;
+}
+#endif

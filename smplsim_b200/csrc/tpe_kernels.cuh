@@ -584,7 +584,7 @@ __device__ __noinline__ int t_solve(const TpeCtx& x, bool any_rows) {
       t_rows<C>(x, lsrch, 4, 0.f, o4);
       float s1 = t_blocksum<C>(x, o4[2]), s2;
       float f0 = g1 + s1, al = 0.f, lo = 0.f, hi = -1.f, tol = 1e-6f * fabsf(f0);
-      bool searching = lsrch && (f0 < 0.f);
+      bool searching = lsrch && (f0 < -W_LS_NOISE * (fabsf(g1) + fabsf(s1)));
       if (searching) al = 1.f;
       for (int ls = 0; ls < TPE_LS_MAXITER; ls++) {
         if (!__syncthreads_or(searching)) break;
@@ -597,6 +597,7 @@ __device__ __noinline__ int t_solve(const TpeCtx& x, bool any_rows) {
             if (f < 0.f) lo = al; else hi = al;
             float an = (fp > 0.f) ? al - f / fp : -1.f;
             if (!(an > lo) || (hi > 0.f && !(an < hi))) an = (hi > 0.f) ? 0.5f * (lo + hi) : 2.f * al;
+            an = fminf(an, W_LS_MAXSTEP);
             if (an == al) searching = false; else al = an;
           }
         }

@@ -18,6 +18,8 @@
 #define W_FULL 0xffffffffu
 #define W_SOLVER_MAXITER 12
 #define W_LS_MAXITER 24
+#define W_LS_NOISE 1e-4f     // line search: directional derivative below this fraction of its two cancelling parts = converged
+#define W_LS_MAXSTEP 16.f    // line search: never extrapolate further than this multiple of the Newton step
 #define W_MAXLIM 8
 
 // ------------------------------------------------------------------ compile-time sizes / shared-memory layout
@@ -624,7 +626,10 @@ __device__ __noinline__ unsigned long long w_collide(const WModel<C>& M, float* 
           float kterm = M.K * imp * pm;
           for (int k = 0; k < 4; k++) sm[C::caref + 4 * c2 + k] = -M.B * dot6(w_wrench(M, cp_s[s], t1, k), v) - kterm;
           // warmset: start from the working set this slot ended the previous substep with (new contacts: all rows active)
-          cflag[c2] = M.warmset ? (1 | ((prevfl[s] & 1) ? (prevfl[s] & 30) : 30)) : 1;
+          {
+            int inh = (M.warmset & 1) ? ((prevfl[s] & 1) ? (prevfl[s] & 30) : ((M.warmset & 2) ? 0 : 30)) : ((M.warmset & 4) ? 30 : 0);
+            cflag[c2] = M.warmset ? (1 | inh) : 1;
+          }
         }
         mask |= 1ull << (g + 1);
         nrows += 4 * cnt;
@@ -740,6 +745,14 @@ __device__ __noinline__ void w_rows(const WModel<C>& M, float* sm, const WLane& 
   out4[0] = g1; out4[1] = g2; out4[2] = s1; out4[3] = s2;
 }
 
+#ifdef SMPLSIM_TRACE
+__device__ float g_trace[8192];
+__device__ int g_trace_n;
+#define W_TRACE(...) do { if (w.live && w.li == 0) { float tv_[] = {__VA_ARGS__}; int n_ = sizeof(tv_) / 4, o_ = atomicAdd(&g_trace_n, n_ + 1); \
+  if (o_ + n_ + 1 <= 8192) { g_trace[o_] = (float)n_; for (int i_ = 0; i_ < n_; i_++) g_trace[o_ + 1 + i_] = tv_[i_]; } } } while (0)
+#else
+#define W_TRACE(...)
+#endif
 // ------------------------------------------------------------------ constraint solve (active-set Newton, each system one ABA); returns extra solves
 template <class C>
 __device__ __noinline__ int w_solve(const WModel<C>& M, float* sm, const WLane& w, bool any_rows) {
@@ -763,11 +776,16 @@ __device__ __noinline__ int w_solve(const WModel<C>& M, float* sm, const WLane& 
     w_outward(M, sm, w, run, 1, 0);
     bool same = w_eval_rows(M, sm, w, run, 1);
     bool fin = run && same, adopt = run && !same && !have_point, lsrch = run && !same && have_point;
+#ifdef SMPLSIM_TRACE
+    { float mx = 0.f; for (int d = 0; d < M.nv; d++) mx = fmaxf(mx, fabsf(sm[C::qstar + d]));
+      int* cf = (int*)(sm + C::cflag); float code = 0.f; for (int c = 0; c < M.nslot; c++) if (cf[c] & 1) code += 1.f;
+      W_TRACE(1.f, (float)it, fin ? 1.f : (adopt ? 2.f : (lsrch ? 3.f : 0.f)), mx, code); }
+#endif
     if (__any_sync(W_FULL, lsrch)) {   // exact line search between the iterate (qacc, acc2) and the trial point (qstar, acc), row space only
       w_rows(M, sm, w, lsrch, 1, 0.f, o4);
       float g1 = w_gsum<C>(o4[0]), g2 = w_gsum<C>(o4[1]), s1 = w_gsum<C>(o4[2]), s2;
       float f0 = g1 + s1, al = 0.f, lo = 0.f, hi = -1.f, tol = 1e-6f * fabsf(f0);
-      bool searching = lsrch && (f0 < 0.f);
+      bool searching = lsrch && (f0 < -W_LS_NOISE * (fabsf(g1) + fabsf(s1)));   // |f0| below the fp32 cancellation floor: converged
       if (searching) al = 1.f;
       for (int ls = 0; ls < W_LS_MAXITER; ls++) {
         if (!__any_sync(W_FULL, searching)) break;
@@ -780,11 +798,13 @@ __device__ __noinline__ int w_solve(const WModel<C>& M, float* sm, const WLane& 
             if (f < 0.f) lo = al; else hi = al;
             float an = (fp > 0.f) ? al - f / fp : -1.f;
             if (!(an > lo) || (hi > 0.f && !(an < hi))) an = (hi > 0.f) ? 0.5f * (lo + hi) : 2.f * al;
+            an = fminf(an, W_LS_MAXSTEP);
             if (an == al) searching = false; else al = an;
           }
         }
       }
       bool step = lsrch && (al > 0.f);
+      W_TRACE(2.f, f0, al, g1, g2);
       if (lsrch && !step) { run = false; iters = it; }
       w_rows(M, sm, w, step, 2, al, o4);
       __syncwarp();
@@ -806,20 +826,20 @@ __device__ __noinline__ int w_solve(const WModel<C>& M, float* sm, const WLane& 
   return iters;
 }
 
-// ------------------------------------------------------------------ stable PD
+// ------------------------------------------------------------------ stable PD   (controllers.py:116-190)
+// ONE ABA per substep: a = (M_s + h Kd)^-1 (-C_s - Kp e - Kd v) with the inertia / bias of the state the FK arrays describe
+// (s = state of the last forward pass, quirk Q1) and e, v of the state currently in qpos / qvel.  Callers run it right after
+// the integration of substep k (FK arrays still at s_k, qpos / qvel already at s_{k+1}), so the torque of substep k+1 is an
+// elementwise formula -- the separate "force-only" solve of the first version is gone.
 template <class C>
 __device__ __noinline__ void w_spd_prepare(const WModel<C>& M, float* sm, const WLane& w) {
-  w_inward(M, sm, w, w.live, W_INERTIA | W_FORCE | W_PB, 1, 1);
+  w_inward(M, sm, w, w.live, W_INERTIA | W_FORCE | W_PB, 2, 1);
   w_outward(M, sm, w, w.live, 2, 0);
 }
 
 template <class C>
 __device__ __noinline__ void w_torque(const WModel<C>& M, float* sm, const WLane& w) {
   int mode = M.cfg.control_mode;
-  if (mode == SMPLSIM_CTRL_UHC_PD) {
-    w_inward(M, sm, w, w.live, W_FORCE, 2, 1);
-    w_outward(M, sm, w, w.live, 1, 0);
-  }
   if (w.live) {
     for (int i = w.li; i < M.nu; i += C::LPE) {
       float a = sm[C::act + i], tq;
@@ -827,7 +847,7 @@ __device__ __noinline__ void w_torque(const WModel<C>& M, float* sm, const WLane
       else {
         float tgt = fmaf(a, M.ascale[i], M.aoffset[i]), q = sm[C::qpos + 7 + i], qd = sm[C::qvel + 6 + i];
         if (mode == SMPLSIM_CTRL_PD) tq = -M.kp[i] * (q - tgt) - M.kd[i] * qd;
-        else tq = -M.kp[i] * (q + qd * M.h - tgt) - M.kd[i] * (qd + (sm[C::spdab + 6 + i] + sm[C::qstar + 6 + i]) * M.h);
+        else tq = -M.kp[i] * (q + qd * M.h - tgt) - M.kd[i] * (qd + sm[C::spdab + 6 + i] * M.h);
       }
       sm[C::tau + i] = fminf(fmaxf(tq, -M.tlim[i]), M.tlim[i]);
     }
@@ -962,6 +982,10 @@ __device__ __noinline__ float w_substeps(const WModel<C>& M, float* sm, const WL
     fo->mask = ((unsigned long long)hi << 32) | lo;
     bool any_rows = w_gany(w.live && nrows > 0, w);
     fo->iters = w_solve(M, sm, w, any_rows);
+#ifdef SMPLSIM_TRACE
+    { float mx = 0.f; for (int d = 0; d < M.nv; d++) mx = fmaxf(mx, fabsf(sm[C::qacc + d]));
+      W_TRACE(0.f, (float)s, (float)fo->iters, (float)nrows, mx, sm[C::qpos + 2]); }
+#endif
     if (s == nsub - 1) {
       if (w.live) {
         for (int b = w.li; b < M.nb; b += C::LPE) {   // framelinvel / frameangvel of the last forward pass (quirk Q2), parked in acc2
@@ -975,8 +999,8 @@ __device__ __noinline__ float w_substeps(const WModel<C>& M, float* sm, const WL
         w_copy<C>(st.qvel_fwd + (size_t)env * M.nv, sm + C::qvel, M.nv, w);
       }
     }
-    if (spd && stale && !raw && (s < nsub - 1 || prep_last)) w_spd_prepare(M, sm, w);
     disp += w_integrate(M, sm, w);
+    if (spd && stale && !raw && (s < nsub - 1 || prep_last)) w_spd_prepare(M, sm, w);   // FK arrays: s_k ; qpos/qvel: s_{k+1}
   }
   return disp;
 }
@@ -1086,12 +1110,13 @@ __global__ void __launch_bounds__(512) k_step3(const DevModel* __restrict__ G, W
     w_copy<C>(sm + C::qvel, a.st.qvel_fwd + eo * M.nv, M.nv, w);
     __syncwarp();
     w_fk(M, sm, w, true);
-    w_spd_prepare(M, sm, w);
   }
   w_copy<C>(sm + C::qpos, a.st.qpos + eo * (M.nv + 1), M.nv + 1, w);
   w_copy<C>(sm + C::qvel, a.st.qvel + eo * M.nv, M.nv, w);
   w_copy<C>(sm + C::qacc, a.st.qacc_warm + eo * M.nv, M.nv, w);
   w_copy<C>(a.mode == 0 ? sm + C::act : sm + C::tau, a.action + eo * M.nu, M.nu, w);
+  __syncwarp();
+  if (spd && M.cfg.spd_stale && a.mode == 0) w_spd_prepare(M, sm, w);
   w_task_io(M, sm, w, a.st, env, false);
   if (a.mode == 0 && w.live && w.li == 0) {
     int* ti = (int*)(sm + C::tsk);
@@ -1171,7 +1196,8 @@ __global__ void __launch_bounds__(512) k_reset3(const DevModel* __restrict__ G, 
   }
   __syncwarp();
   if (init == SMPLSIM_INIT_FALL) {
-    if (c.control_mode == SMPLSIM_CTRL_UHC_PD && c.spd_stale) { w_fk(M, sm, w, true); w_spd_prepare(M, sm, w); }   // mj_forward
+    const bool spd_st = (c.control_mode == SMPLSIM_CTRL_UHC_PD && c.spd_stale);
+    if (spd_st) w_fk(M, sm, w, true);   // mj_forward: inertia / bias of the initial state
     int ngrp = (M.nu + 3) / 4;
     for (int k3 = 0; k3 < 3; k3++) {
       int* ti = (int*)(sm + C::tsk);
@@ -1186,7 +1212,8 @@ __global__ void __launch_bounds__(512) k_reset3(const DevModel* __restrict__ G, 
       __syncwarp();
       if (w.live && w.li == 0) ti[W_TSK_RNG] = (int)(base + (uint32_t)ngrp);
       __syncwarp();
-      w_substeps(M, sm, w, c.nsubsteps, 0, &fo, a.st, env, false, true, 0);
+      if (spd_st) w_spd_prepare(M, sm, w);   // factors of the last forward pass, PD error of the current state and the new action
+      w_substeps(M, sm, w, c.nsubsteps, 0, &fo, a.st, env, false, false, 0);
     }
   }
   // reset_sim(): mj_forward at the reset state

@@ -350,3 +350,26 @@ def test_spd_fresh_mode_runs_and_differs_slightly():
         assert np.isfinite(outs[spd]).all()
     d = np.abs(outs["stale"] - outs["fresh"]).max()
     assert 0 < d < 5e-2, d
+
+
+def test_regression_line_search_noise_floor():
+    """Captured case (round 1): from the Default reset pose with this action, substep 7's active-set iterate was already
+    optimal to fp32 rounding but one row sat at r ~ 0, so the set comparison asked for another line search; its directional
+    derivative (-3e-6, pure cancellation noise against g1 = 0.076) and curvature (-3e-6) sent the step to 2^24 and the env
+    blew up (max|qvel| 281 instead of 3.62).  The solver now treats |f0| below the cancellation floor as converged and
+    caps the extrapolation; the step must match the oracle replay."""
+    d = np.load(os.path.join(GOLDEN, "regress_default_step_case1.npz"))
+    cfg, om = make_models(env="speed")
+    env = _batch(cfg, 64, seed=0)
+    env.reset()
+    env.task_change_step.fill_(10 ** 6)   # the speed target only enters obs / reward
+    e = orc.OracleEnv(om, env_id=0)
+    e.reset()
+    assert np.abs(env.qpos[0].cpu().numpy() - d["qpos"]).max() < 1e-6
+    act = np.repeat(d["action"][None], 64, 0)
+    env.step(_t(act))
+    e.step(d["action"].astype(np.float64))
+    qp, qv = env.qpos.cpu().numpy(), env.qvel.cpu().numpy()
+    assert np.array_equal(qp, np.repeat(qp[:1], 64, 0))
+    assert relerr(qv[0], e.qvel) < 2e-3 and relerr(qp[0], e.qpos) < 2e-4, (relerr(qv[0], e.qvel), relerr(qp[0], e.qpos))
+    assert np.abs(qv).max() < 5.0
