@@ -131,6 +131,9 @@ typedef struct SmplsimAux {
   float* qacc;          /* [N,nv] */
   float* ctrl;          /* [N,nu] torque applied in the last substep */
   int32_t* solver_iter; /* [N]   constraint-solver iterations of the last substep */
+  uint8_t* status;      /* [N]   mj_warning bits raised during this call (OR over substeps): 1 BADQPOS, 2 BADQVEL, 4 BADQACC.
+                         *       As in mj_step (mj_checkPos/Vel/Acc + mj_resetData) a NaN or |x| > 1e10 auto-resets that env's
+                         *       data to qpos0 / zero velocity and the call carries on -- a device fault never traps. */
 } SmplsimAux;
 
 typedef struct SmplsimHandle SmplsimHandle;

@@ -177,6 +177,7 @@ class OracleEnv:
     cur_t = property(lambda s: lib().orc_get_int(s.ptr, 0), lambda s, v: lib().orc_set_int(s.ptr, 0, int(v)))
     change_step = property(lambda s: lib().orc_get_int(s.ptr, 1), lambda s, v: lib().orc_set_int(s.ptr, 1, int(v)))
     recovery = property(lambda s: lib().orc_get_int(s.ptr, 2), lambda s, v: lib().orc_set_int(s.ptr, 2, int(v)))
+    warn = property(lambda s: lib().orc_get_int(s.ptr, 4), lambda s, v: lib().orc_set_int(s.ptr, 4, int(v)))   # sticky mj_warning bits (1 qpos, 2 qvel, 4 qacc)
     rng_counter = property(lambda s: lib().orc_get_int(s.ptr, 3) & 0xFFFFFFFF, lambda s, v: lib().orc_set_int(s.ptr, 3, int(v)))
 
     def observations(self):

@@ -78,14 +78,15 @@ class HumanoidBatchB200:
         self.qacc = torch.zeros(N, m.nv, **f32)
         self.ctrl = torch.zeros(N, m.nu, **f32)
         self.solver_iter = torch.zeros(N, **i32)
-        self.extras = {"terminate": self.terminate_buf}
+        self.status = torch.zeros(N, dtype=torch.uint8, device=dv)   # mj_warning bits of the last call (1 qpos, 2 qvel, 4 qacc)
+        self.extras = {"terminate": self.terminate_buf, "sim_warning": self.status}
         self._state = SmplsimStateC(*[t.data_ptr() for t in (self.qpos, self.qvel, self.qpos_fwd, self.qvel_fwd, self.qacc_warm,
                                                              self.task_target, self.task_change_step, self.progress_buf,
                                                              self.recovery, self.rng_counter)])
         self._aux = SmplsimAuxC(*[t.data_ptr() for t in (self.xpos, self.xquat, self.body_linvel, self.body_angvel,
-                                                         self.contact_mask, self.qacc, self.ctrl, self.solver_iter)])
-        if not with_aux:        # throughput runs: skip the side outputs (all-NULL SmplsimAux)
-            self._aux = SmplsimAuxC()
+                                                         self.contact_mask, self.qacc, self.ctrl, self.solver_iter, self.status)])
+        if not with_aux:        # throughput runs: skip the side outputs (NULL pointers), keep the 1-byte status
+            self._aux = SmplsimAuxC(status=self.status.data_ptr())
         self.gpu_launches = 0
 
     def __del__(self):
@@ -180,7 +181,7 @@ class HumanoidBatchB200:
 
     @property
     def kernel_version(self) -> int:
-        """2: chain-lane kernels (4 lanes per env); 1: generic warp-per-env kernels (SMPLSIM_KERNEL=v1 forces them)."""
+        """3: default warp kernels (warp_kernels.cuh); 1: generic warp-per-env fallback; 2 / 4: experimental (SMPLSIM_KERNEL)."""
         return _lib.lib().smplsim_kernel_version(self._h)
 
     @property

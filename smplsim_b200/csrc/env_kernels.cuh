@@ -83,6 +83,26 @@ __device__ void reset_task(const DevModel& M, const EnvLayout& L, float* sm, int
   ti[TSK_CHANGE] = ti[TSK_CURT] + rand_range(r[3], c.change_steps_min, c.change_steps_max);
 }
 
+// mj_checkPos / mj_checkVel (what 0) and mj_checkAcc (what 1) with mj_resetData, SURVEY A.2 (see w_check in warp_kernels.cuh)
+__device__ int check_state(const DevModel& M, const EnvLayout& L, float* sm, int lane, int what) {
+  bool b0 = false, b1 = false;
+  if (what == 0) {
+    for (int i = lane; i < M.nq; i += 32) b0 |= !(fabsf(sm[L.qpos + i]) <= 1e10f);
+    for (int i = lane; i < M.nv; i += 32) b1 |= !(fabsf(sm[L.qvel + i]) <= 1e10f);
+  } else {
+    for (int i = lane; i < M.nv; i += 32) b0 |= !(fabsf(sm[L.qacc + i]) <= 1e10f);
+  }
+  b0 = __any_sync(0xffffffffu, b0); b1 = __any_sync(0xffffffffu, b1);
+  int bits = (what == 0) ? (b0 ? 1 : (b1 ? 2 : 0)) : (b0 ? 4 : 0);
+  if (bits) {
+    for (int i = lane; i < M.nq; i += 32) sm[L.qpos + i] = (i < 3) ? M.bpos[0][i] : (i < 7) ? M.bquat[0][i - 3] : 0.f;
+    for (int i = lane; i < M.nv; i += 32) { sm[L.qvel + i] = 0.f; sm[L.qacc + i] = 0.f; sm[L.qwarm + i] = 0.f; }
+    for (int i = lane; i < M.nu; i += 32) sm[L.tau + i] = 0.f;
+  }
+  __syncwarp();
+  return bits;
+}
+
 // nsub x [compute_torque + mj_step] on the staged state.  ctrl_mode: 0 = controller on `act`, 1 = tau preset.
 // Returns (lanes 0..2) the root displacement; mask/iters of the last forward pass through `last`.
 __device__ float run_substeps(const DevModel& M, const EnvLayout& L, float* sm, int lane, int nsub, int raw, FwdOut& last,
@@ -90,16 +110,32 @@ __device__ float run_substeps(const DevModel& M, const EnvLayout& L, float* sm, 
   const bool spd = (M.cfg.control_mode == SMPLSIM_CTRL_UHC_PD);
   const bool stale = M.cfg.spd_stale != 0;
   float disp = 0.f;
+  bool restore = false;
   for (int s = 0; s < nsub; s++) {
     bool did_fk = false;
     if (!raw) {
       if (spd && !stale) { fk_pass<true>(M, L, sm, lane); spd_prepare(M, L, sm, lane); did_fk = true; }
       compute_torque(M, L, sm, lane);
+    } else if (restore) {
+      for (int i = lane; i < M.nu; i += 32) sm[L.tau + i] = sm[L.act + i];
+      restore = false;
+      __syncwarp();
     }
+    int bad = check_state(M, L, sm, lane, 0);
+    if (bad) did_fk = false;
     if (!did_fk) fk_pass<true>(M, L, sm, lane);
     last.mask = collide(M, L, sm, lane);
     int nlim = make_limits(M, L, sm, lane);
     last.iters = solve_constrained(M, L, sm, lane, (last.mask != 0ull) || (nlim > 0));
+    if (check_state(M, L, sm, lane, 1)) {   // mj_checkAcc: forward again on the reset data
+      bad |= 4;
+      fk_pass<true>(M, L, sm, lane);
+      last.mask = collide(M, L, sm, lane);
+      nlim = make_limits(M, L, sm, lane);
+      last.iters = solve_constrained(M, L, sm, lane, (last.mask != 0ull) || (nlim > 0));
+    }
+    last.status |= bad;
+    if (raw && bad) restore = true;
     if (s == nsub - 1) {
       for (int b = lane; b < M.nb; b += 32) {   // sensors of the last forward pass (quirk Q2)
         S6 v = ld6(sm + L.vel + 6 * b);
@@ -185,6 +221,7 @@ __device__ void write_aux(const DevModel& M, const EnvLayout& L, float* sm, int 
   if (lane == 0) {
     if (aux.contact_mask) aux.contact_mask[env] = fo.mask;
     if (aux.solver_iter) aux.solver_iter[env] = fo.iters;
+    if (aux.status) aux.status[env] = (uint8_t)fo.status;
   }
 }
 
@@ -211,14 +248,15 @@ __global__ void __launch_bounds__(32 * SM_WARPS_PER_BLOCK) k_step(const DevModel
   load_row(sm + L.qpos, a.st.qpos + (size_t)env * M.nq, M.nq, lane);
   load_row(sm + L.qvel, a.st.qvel + (size_t)env * M.nv, M.nv, lane);
   load_row(sm + L.qwarm, a.st.qacc_warm + (size_t)env * M.nv, M.nv, lane);
-  load_row(a.mode == 0 ? sm + L.act : sm + L.tau, a.action + (size_t)env * M.nu, M.nu, lane);
+  load_row(sm + L.act, a.action + (size_t)env * M.nu, M.nu, lane);
+  if (a.mode != 0) load_row(sm + L.tau, a.action + (size_t)env * M.nu, M.nu, lane);
   load_task(M, L, sm, lane, a.st, env);
   if (a.mode == 0 && lane == 0) {   // pre_physics_step -> update_task (humanoid_task.py:26-28)
     int* ti = (int*)(sm + L.tsk);
     if (M.cfg.task != SMPLSIM_TASK_NONE && ti[TSK_CURT] >= ti[TSK_CHANGE]) reset_task(M, L, sm, env);
   }
   __syncwarp();
-  FwdOut fo; fo.mask = 0ull; fo.iters = 0;
+  FwdOut fo; fo.mask = 0ull; fo.iters = 0; fo.status = 0;
   float disp = run_substeps(M, L, sm, lane, a.nsub, a.mode, fo, a.st, env, true, false);
   // ---- post_physics_step
   fk_pass<false>(M, L, sm, lane);   // mj_kinematics at the integrated state (humanoid_env.py:389)
@@ -279,7 +317,7 @@ __global__ void __launch_bounds__(32 * SM_WARPS_PER_BLOCK) k_reset(const DevMode
   for (int i = lane; i < M.nv; i += 32) { sm[L.qvel + i] = 0.f; sm[L.qwarm + i] = 0.f; sm[L.qacc + i] = 0.f; }
   for (int i = lane; i < M.nu; i += 32) sm[L.tau + i] = 0.f;
   __syncwarp();
-  FwdOut fo; fo.mask = 0ull; fo.iters = 0;
+  FwdOut fo; fo.mask = 0ull; fo.iters = 0; fo.status = 0;
   if (init == SMPLSIM_INIT_DEFAULT) {
     if (lane == 0) { sm[L.qpos + 2] = 0.94f; sm[L.qpos + 3] = 0.5f; sm[L.qpos + 4] = 0.5f; sm[L.qpos + 5] = 0.5f; sm[L.qpos + 6] = 0.5f; }
   } else if (init == SMPLSIM_INIT_FALL) {

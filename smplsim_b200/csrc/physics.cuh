@@ -618,9 +618,9 @@ __device__ void compute_torque(const DevModel& M, const EnvLayout& L, float* sm,
 }
 
 // ------------------------------------------------------------------ mj_forward at the current state (tau given) -> qacc, sensors, contact mask
-struct FwdOut { unsigned long long mask; int iters; };
+struct FwdOut { unsigned long long mask; int iters; int status; };
 __device__ FwdOut forward_dynamics(const DevModel& M, const EnvLayout& L, float* sm, int lane) {
-  FwdOut o;
+  FwdOut o; o.status = 0;
   fk_pass<true>(M, L, sm, lane);
   o.mask = collide(M, L, sm, lane);
   int nlim = make_limits(M, L, sm, lane);

@@ -959,13 +959,40 @@ __device__ __noinline__ void w_reset_task(const WModel<C>& M, float* sm, int env
   ti[W_TSK_CHANGE] = ti[W_TSK_CURT] + rand_range(r[3], c.change_steps_min, c.change_steps_max);
 }
 
-struct WFwd { unsigned long long mask; int iters; };
+// mj_checkPos / mj_checkVel (what 0, before the forward pass) and mj_checkAcc (what 1, after the solve), SURVEY A.2
+// ([MJ-upstream] engine_forward.c): a NaN or |x| > mjMAXVAL = 1e10 raises the warning bit and auto-resets the env's data like
+// mj_resetData (qpos = qpos0, qvel = ctrl = qacc_warmstart = 0).  Returns the warning bits of this lane's env (1 qpos | 2 qvel | 4 qacc).
+#define W_MAXVAL 1e10f
+template <class C>
+__device__ __noinline__ int w_check(const WModel<C>& M, float* sm, const WLane& w, int what) {
+  bool b0 = false, b1 = false;
+  if (w.live) {
+    if (what == 0) {
+      for (int i = w.li; i < M.nv + 1; i += C::LPE) b0 |= !(fabsf(sm[C::qpos + i]) <= W_MAXVAL);
+      for (int i = w.li; i < M.nv; i += C::LPE) b1 |= !(fabsf(sm[C::qvel + i]) <= W_MAXVAL);
+    } else {
+      for (int i = w.li; i < M.nv; i += C::LPE) b0 |= !(fabsf(sm[C::qacc + i]) <= W_MAXVAL);
+    }
+  }
+  b0 = w_gany(b0, w); b1 = w_gany(b1, w);
+  int bits = (what == 0) ? (b0 ? 1 : (b1 ? 2 : 0)) : (b0 ? 4 : 0);
+  if (bits && w.live) {
+    for (int i = w.li; i < M.nv + 1; i += C::LPE) sm[C::qpos + i] = (i < 3) ? M.bpos[0][i] : (i < 7) ? M.bquat[0][i - 3] : 0.f;
+    for (int i = w.li; i < M.nv; i += C::LPE) { sm[C::qvel + i] = 0.f; sm[C::qacc + i] = 0.f; }
+    for (int i = w.li; i < M.nu; i += C::LPE) sm[C::tau + i] = 0.f;
+  }
+  __syncwarp();
+  return bits;
+}
+
+struct WFwd { unsigned long long mask; int iters; int status; };
 
 template <class C>
 __device__ __noinline__ float w_substeps(const WModel<C>& M, float* sm, const WLane& w, int nsub, int raw, WFwd* fo, const SmplsimState& st, int env,
                                          bool write_fwd, bool prep_last, int align) {
   const bool spd = (M.cfg.control_mode == SMPLSIM_CTRL_UHC_PD), stale = M.cfg.spd_stale != 0;
   float disp = 0.f;
+  bool restore = false;   // raw mode: the caller's ctrl (kept in act) comes back the substep after an auto-reset zeroed it
   for (int s = 0; s < nsub; s++) {
     // keep the warps of a CTA in the same phase: the hot code of one phase fits the instruction cache, that of
     // 14 drifting warps does not (round-1 profile: "no_instruction" was the top stall)
@@ -974,7 +1001,13 @@ __device__ __noinline__ float w_substeps(const WModel<C>& M, float* sm, const WL
     if (!raw) {
       if (spd && !stale) { w_fk(M, sm, w, true); w_spd_prepare(M, sm, w); did_fk = true; }
       w_torque(M, sm, w);
+    } else if (__any_sync(W_FULL, restore)) {
+      if (w.live && restore) for (int i = w.li; i < M.nu; i += C::LPE) sm[C::tau + i] = sm[C::act + i];
+      restore = false;
+      __syncwarp();
     }
+    int bad = w_check(M, sm, w, 0);
+    if (__any_sync(W_FULL, bad != 0)) did_fk = false;
     if (!did_fk) w_fk(M, sm, w, true);
     int nrows = 0;
     unsigned long long m = w_collide(M, sm, w, &nrows);
@@ -982,10 +1015,21 @@ __device__ __noinline__ float w_substeps(const WModel<C>& M, float* sm, const WL
     fo->mask = ((unsigned long long)hi << 32) | lo;
     bool any_rows = w_gany(w.live && nrows > 0, w);
     fo->iters = w_solve(M, sm, w, any_rows);
-#ifdef SMPLSIM_TRACE
-    { float mx = 0.f; for (int d = 0; d < M.nv; d++) mx = fmaxf(mx, fabsf(sm[C::qacc + d]));
-      W_TRACE(0.f, (float)s, (float)fo->iters, (float)nrows, mx, sm[C::qpos + 2]); }
-#endif
+    int badacc = w_check(M, sm, w, 1);
+    if (__any_sync(W_FULL, badacc != 0)) {   // mj_checkAcc: forward pass again on the reset data, then integrate
+      WLane w2 = w;
+      w2.live = w.live && badacc != 0;
+      w_fk(M, sm, w2, true);
+      int nrows2 = 0;
+      unsigned long long m2 = w_collide(M, sm, w2, &nrows2);
+      unsigned lo2 = w_gor<C>((unsigned)(m2 & 0xffffffffull)), hi2 = w_gor<C>((unsigned)(m2 >> 32));
+      bool any2 = w_gany(w2.live && nrows2 > 0, w2);
+      int it2 = w_solve(M, sm, w2, any2);
+      if (badacc) { fo->mask = ((unsigned long long)hi2 << 32) | lo2; fo->iters = it2; }
+    }
+    bad |= badacc;
+    fo->status |= bad;
+    if (raw && bad) restore = true;
     if (s == nsub - 1) {
       if (w.live) {
         for (int b = w.li; b < M.nb; b += C::LPE) {   // framelinvel / frameangvel of the last forward pass (quirk Q2), parked in acc2
@@ -1075,6 +1119,7 @@ __device__ __noinline__ void w_write_aux(const WModel<C>& M, float* sm, const WL
   if (w.li == 0) {
     if (aux.contact_mask) aux.contact_mask[env] = fo.mask;
     if (aux.solver_iter) aux.solver_iter[env] = fo.iters;
+    if (aux.status) aux.status[env] = (uint8_t)fo.status;
   }
 }
 
@@ -1114,7 +1159,8 @@ __global__ void __launch_bounds__(512) k_step3(const DevModel* __restrict__ G, W
   w_copy<C>(sm + C::qpos, a.st.qpos + eo * (M.nv + 1), M.nv + 1, w);
   w_copy<C>(sm + C::qvel, a.st.qvel + eo * M.nv, M.nv, w);
   w_copy<C>(sm + C::qacc, a.st.qacc_warm + eo * M.nv, M.nv, w);
-  w_copy<C>(a.mode == 0 ? sm + C::act : sm + C::tau, a.action + eo * M.nu, M.nu, w);
+  w_copy<C>(sm + C::act, a.action + eo * M.nu, M.nu, w);
+  if (a.mode != 0) w_copy<C>(sm + C::tau, a.action + eo * M.nu, M.nu, w);   // raw ctrl (act keeps a copy for the substep after an auto-reset)
   __syncwarp();
   if (spd && M.cfg.spd_stale && a.mode == 0) w_spd_prepare(M, sm, w);
   w_task_io(M, sm, w, a.st, env, false);
@@ -1123,7 +1169,7 @@ __global__ void __launch_bounds__(512) k_step3(const DevModel* __restrict__ G, W
     if (M.cfg.task != SMPLSIM_TASK_NONE && ti[W_TSK_CURT] >= ti[W_TSK_CHANGE]) w_reset_task(M, sm, env);
   }
   __syncwarp();
-  WFwd fo; fo.mask = 0ull; fo.iters = 0;
+  WFwd fo; fo.mask = 0ull; fo.iters = 0; fo.status = 0;
   float disp = w_substeps(M, sm, w, a.nsub, a.mode, &fo, a.st, env, true, false, a.align);
   w_fk(M, sm, w, false);
   if (a.mode == 0) {
@@ -1174,7 +1220,7 @@ __global__ void __launch_bounds__(512) k_reset3(const DevModel* __restrict__ G, 
   if (w.live && w.li == 0) {
     int* ti = (int*)(sm + C::tsk);
     ((int*)sm)[C::lim] = 0;
-    for (int c = 0; c < M.nslot; c++) ((int*)sm)[C::cflag + c] = 0;
+    for (int cs = 0; cs < M.nslot; cs++) ((int*)sm)[C::cflag + cs] = 0;
     if (c.task == SMPLSIM_TASK_GETUP) ti[W_TSK_RECOV] = c.recovery_steps;
     if (!c.legacy_change_step) ti[W_TSK_CURT] = 0;
     w_reset_task(M, sm, env);   // sees the old cur_t when legacy_change_step (quirk Q4)
@@ -1185,7 +1231,7 @@ __global__ void __launch_bounds__(512) k_reset3(const DevModel* __restrict__ G, 
     for (int i = w.li; i < M.nu; i += C::LPE) { sm[C::tau + i] = 0.f; sm[C::act + i] = 0.f; }
   }
   __syncwarp();
-  WFwd fo; fo.mask = 0ull; fo.iters = 0;
+  WFwd fo; fo.mask = 0ull; fo.iters = 0; fo.status = 0;
   if (init == SMPLSIM_INIT_MOCAP) {
     w_copy<C>(sm + C::qpos, a.qpos0 + eo * (M.nv + 1), M.nv + 1, w);
     w_copy<C>(sm + C::qvel, a.qvel0 + eo * M.nv, M.nv, w);

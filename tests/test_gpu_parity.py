@@ -187,11 +187,17 @@ def test_controller_torque_matches_oracle(mode):
     env.task_change_step.fill_(10000)
     env.step(_t(act))
     gt = env.ctrl.cpu().numpy()
+    st = env.status.cpu().numpy()
+    assert (st != 0).sum() <= 2
     for i in range(n):
         e = orc.OracleEnv(om)
         e.qpos[:] = qs[i]; e.qvel[:] = v[i] * 0.9; e.forward()       # leaves M, qfrc_bias of the stale state
         e.qpos[:] = q[i]; e.qvel[:] = v[i]
         tau = e.compute_torque(act[i])
+        if st[i]:        # a blown-up rollout state (|qvel| ~ 1e5): mj_checkAcc resets the data and zeroes ctrl, in the oracle too
+            e.ctrl[:] = tau; e.warn = 0; e.mj_step()
+            assert e.warn == st[i] and np.abs(gt[i]).max() == 0.0
+            continue
         scale = max(1.0, np.abs(tau).max())
         assert np.abs(gt[i] - tau).max() / scale < 2e-4, (i, np.abs(gt[i] - tau).max(), scale)
 
@@ -373,3 +379,38 @@ def test_regression_line_search_noise_floor():
     assert np.array_equal(qp, np.repeat(qp[:1], 64, 0))
     assert relerr(qv[0], e.qvel) < 2e-3 and relerr(qp[0], e.qpos) < 2e-4, (relerr(qv[0], e.qvel), relerr(qp[0], e.qpos))
     assert np.abs(qv).max() < 5.0
+
+
+@pytest.mark.parametrize("case", ["nan_qpos", "huge_qvel", "bad_qacc"])
+def test_bad_state_autoreset_matches_mj_step_semantics(case):
+    """mj_checkPos / mj_checkVel / mj_checkAcc + mj_resetData: a NaN or |x| > 1e10 never reaches the caller --
+    the env's data is reset to qpos0 / zero velocity inside the substep, the warning bit is reported in aux.status, and the
+    rest of the env step proceeds from there exactly like the oracle."""
+    cfg, om = make_models(env="speed")
+    m = om.model
+    n = 8
+    env = _batch(cfg, n, seed=0)
+    env.reset()
+    e = orc.OracleEnv(om, env_id=3)
+    e.reset()
+    qp, qv = env.qpos.clone(), env.qvel.clone()
+    if case == "nan_qpos":
+        qp[3, 20] = float("nan"); e.qpos[20] = np.nan; bit = 1
+    elif case == "huge_qvel":
+        qv[3, 10] = 3e10; e.qvel[10] = 3e10; bit = 2
+    else:
+        qv[3, 6:] = 8e9; e.qvel[6:] = 8e9; bit = 4          # finite state, velocity-product forces overflow 1e10
+    env.set_state(qp, qv)
+    e.forward()
+    act = np.zeros((n, m.nu)); act[:] = 0.05
+    obs, rew, term, trunc = env.step(_t(act))
+    st = env.status.cpu().numpy()
+    e.warn = 0
+    o, r, te, tr = e.step(act[3])
+    assert e.warn & bit, e.warn
+    assert st[3] & bit and not st[[0, 1, 2, 4, 5, 6, 7]].any(), st
+    assert torch.isfinite(env.qpos).all() and torch.isfinite(env.qvel).all() and torch.isfinite(obs).all()
+    assert relerr(env.qpos[3].cpu().numpy(), e.qpos) < 1e-3 and relerr(env.qvel[3].cpu().numpy(), e.qvel) < 5e-3
+    ref = env.qpos[0].cpu().numpy()
+    for i in (1, 2, 4, 5, 6, 7):                            # neighbours in the same CTA are untouched
+        assert np.array_equal(env.qpos[i].cpu().numpy(), ref)

@@ -101,3 +101,31 @@ def test_controllers_match_reference(mode, key, ps):
 def test_philox_known_answer():
     # Random123 KAT: philox4x32-10, counter 0, key 0
     assert orc.philox(0, 0, 0) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+
+
+def test_oracle_bad_state_autoreset():
+    """mj_checkPos / mj_checkVel / mj_checkAcc + mj_resetData semantics: warning bit, reset to qpos0, finite afterwards."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from util_states import make_models
+    cfg, om = make_models(env="speed")
+    m = om.model
+    for case, bit in (("qpos", 1), ("qvel", 2), ("qacc", 4)):
+        e = orc.OracleEnv(om, env_id=1)
+        e.reset()
+        if case == "qpos":
+            e.qpos[20] = np.nan
+        elif case == "qvel":
+            e.qvel[10] = -3e10
+        else:
+            e.qvel[6:] = 8e9
+        e.warn = 0
+        e.ctrl[:] = 0.0
+        e.mj_step()
+        assert e.warn == bit
+        assert np.isfinite(e.qpos).all() and np.isfinite(e.qvel).all()
+        assert abs(e.qpos[3] - 1.0) < 1e-3 and np.abs(e.qpos[7:]).max() < 1e-2     # one substep away from qpos0
+    e = orc.OracleEnv(om, env_id=1)
+    e.reset(); e.warn = 0
+    e.step(np.zeros(m.nu))
+    assert e.warn == 0
