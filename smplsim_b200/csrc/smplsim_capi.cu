@@ -256,6 +256,7 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
     }
     const char* ws = std::getenv("SMPLSIM_WARMSET");
     m.warmset = ws ? std::atoi(ws) : 1;
+    { const char* dp = std::getenv("SMPLSIM_DIRTYPATH"); m.dirtypath = dp ? std::atoi(dp) : 1; }
     const char* rp = std::getenv("SMPLSIM_ROWS");
     m.rowpar = rp ? std::atoi(rp) : 0;   // opt-in: measured slower than the level sweeps in round 1 (profiles/r1_k_step3_rows.md)
   }
@@ -345,6 +346,7 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
     const char* lpe = std::getenv("SMPLSIM_LPE");
     const char* al = std::getenv("SMPLSIM_ALIGN");
     if (al) h->align3 = std::atoi(al);
+    if (const char* ag = std::getenv("SMPLSIM_ALIGN_GROUP")) h->align3 = (h->align3 & 255) | (std::atoi(ag) << 8);   // warps per barrier group
     const char* wp = std::getenv("SMPLSIM_WPB");
     h->wpb3 = wp ? std::atoi(wp) : 0;
     bool want = !force || std::string(force) == "v3" || std::string(force) == "v4";

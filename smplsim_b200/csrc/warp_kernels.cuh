@@ -42,7 +42,7 @@ struct WCfg {
 // constants staged per CTA (float32 image of the model, exact sizes)
 template <class C>
 struct WModel {
-  int nb, nv, nu, ng, nlevel, nslot, sched_T, rowpar, warmset;
+  int nb, nv, nu, ng, nlevel, nslot, sched_T, rowpar, warmset, dirtypath;
   int sched[SM_MAXSCHED][4], sched_nd[SM_MAXSCHED], sched_nc[SM_MAXSCHED], sched_ns[SM_MAXSCHED];
   int parent[C::NB], dofadr[C::NB], dofnum[C::NB];
   int level_adr[SM_MAXL + 1], level_list[C::NB], child_adr[C::NB + 1], child_list[C::NB];
@@ -68,7 +68,7 @@ __device__ void w_stage_model(const DevModel* __restrict__ G, WModel<C>& M) {
     for (int i = 0; i < 5; i++) M.solimp[i] = G->solimp[i];
     M.imp_a = G->imp_a; M.imp_b = G->imp_b; M.K = G->K; M.B = G->B; M.h = G->h; M.legal_mask = G->legal_mask; M.cfg = G->cfg;
     M.obs_dim = G->obs_dim; M.self_obs_dim = G->self_obs_dim;
-    M.sched_T = G->sched_T; M.rowpar = G->rowpar; M.warmset = G->warmset;
+    M.sched_T = G->sched_T; M.rowpar = G->rowpar; M.warmset = G->warmset; M.dirtypath = G->dirtypath;
     for (int i = 0; i < SM_MAXSCHED; i++) {
       for (int k = 0; k < 4; k++) M.sched[i][k] = G->sched[i][k];
       M.sched_nd[i] = G->sched_nd[i]; M.sched_nc[i] = G->sched_nc[i]; M.sched_ns[i] = G->sched_ns[i];
@@ -135,7 +135,7 @@ __device__ __forceinline__ void w_sincos(float x, float* s, float* c) {
 }
 
 template <class C>
-__device__ __forceinline__ float w_impedance(const WModel<C>& M, float pm) {
+__device__ __noinline__ float w_impedance(const WModel<C>& M, float pm) {
   float x = fabsf(pm) / fmaxf(M.solimp[2], 1e-15f);
   if (x >= 1.f) return M.solimp[1];
   if (x <= 0.f) return M.solimp[0];
@@ -442,7 +442,9 @@ __device__ __noinline__ void w_outward8(const WModel<C>& M, float* sm, const WLa
 // ------------------------------------------------------------------ ABA inward sweep
 // flags: 1 INERTIA | 2 FORCE | 4 PB | 8 CONTACTS ; tmode: 0 tau (+limit rows) | 1 zero | 2 stable-PD -kp e - kd qd ; dmode: 0 armature (+limit rows) | 1 + h kd
 template <class C>
-__device__ __noinline__ void w_inward(const WModel<C>& M, float* sm, const WLane& w, bool run, int flags, int tmode, int dmode) {
+__device__ __noinline__ void w_inward(const WModel<C>& M, float* sm, const WLane& w, bool run, int flags, int tmode, int dmode, unsigned long long only = 0ull) {
+  // only != 0: recompute just the bodies in the mask (solver iterations >= 2: sub-trees without constraint rows keep the
+  // articulated inertia / bias force of the first iteration, they do not depend on the working set)
   if (C::LPE == 32 && M.rowpar && M.sched_T > 0) { w_inward8(M, sm, w, run, flags, tmode, dmode); return; }
   const bool inertia = flags & W_INERTIA, force = flags & W_FORCE;
   const int nlim = (tmode == 0 || dmode == 0) ? ((const int*)sm)[C::lim] : 0;
@@ -450,6 +452,7 @@ __device__ __noinline__ void w_inward(const WModel<C>& M, float* sm, const WLane
     if (run) {
       for (int i = M.level_adr[lev] + w.li; i < M.level_adr[lev + 1]; i += C::LPE) {
         int b = M.level_list[i];
+        if (only && !((only >> b) & 1ull)) continue;
         float A[21];
         S6 p = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
         if (inertia) rb_expand(sm + C::irb + 10 * b, A);
@@ -582,13 +585,11 @@ __device__ __noinline__ unsigned long long w_collide(const WModel<C>& M, float* 
       V3 c = ld3(sm + C::xpos + 3 * b) + mrot(R, ld3(M.gpos[g]));
       float d0 = h0 + dot(n, c);
       int s0 = M.slot_adr[g], s1 = M.slot_adr[g + 1], cnt = 0;
-      int prevfl[4] = {0, 0, 0, 0};
-      for (int s = s0; s < s1; s++) { if (s - s0 < 4) prevfl[s - s0] = cflag[s]; cflag[s] = 0; }
       const float* gm = M.gmat[g];
       int ty = M.gtype[g];
       V3 t1 = ld3(M.t1_default);
-      float dist_s[4];
-      V3 cp_s[4];
+      // pass 1: contact points straight into the slot arrays (cD holds the distance until pass 2); loops kept rolled --
+      // this function runs once per substep and its footprint, not its instruction count, is what costs (instruction cache)
       if (ty == SMPLSIM_GEOM_CAPSULE || ty == SMPLSIM_GEOM_SPHERE) {
         V3 axw = mrot(R, v3(gm[2], gm[5], gm[8]));
         float rad = M.gsize[g][0], hl = (ty == SMPLSIM_GEOM_CAPSULE) ? M.gsize[g][1] : 0.f, na = dot(n, axw);
@@ -598,42 +599,47 @@ __device__ __noinline__ unsigned long long w_collide(const WModel<C>& M, float* 
           float nn = sqrtf(dot(t1, t1));
           t1 = (nn < 1e-15f) ? v3(1.f, 0.f, 0.f) : (1.0f / nn) * t1;
         }
+#pragma unroll 1
         for (int e = 0; e < nend; e++) {
           float sg = e ? -hl : hl, dist = d0 + sg * na - rad;
           if (dist > M.margin) continue;
-          cp_s[cnt] = c + sg * axw - (rad + 0.5f * dist) * n; dist_s[cnt] = dist; cnt++;
+          st3(sm + C::cpos + 3 * (s0 + cnt), c + sg * axw - (rad + 0.5f * dist) * n); sm[C::cD + s0 + cnt] = dist; cnt++;
         }
       } else {
+#pragma unroll 1
         for (int i = 0; i < 8 && cnt < 4; i++) {
           V3 vl = v3((i & 1) ? M.gsize[g][0] : -M.gsize[g][0], (i & 2) ? M.gsize[g][1] : -M.gsize[g][1], (i & 4) ? M.gsize[g][2] : -M.gsize[g][2]);
           V3 wv = mrot(R, mrot(gm, vl));
           float l = dot(n, wv);
           if (d0 + l > M.margin || l > 0.f) continue;
           float dist = d0 + l;
-          cp_s[cnt] = c + wv - (0.5f * dist) * n; dist_s[cnt] = dist; cnt++;
+          st3(sm + C::cpos + 3 * (s0 + cnt), c + wv - (0.5f * dist) * n); sm[C::cD + s0 + cnt] = dist; cnt++;
         }
       }
       if (cnt) {
         st3(sm + C::ct1 + 3 * g, t1);
         S6 v = ld6(sm + C::vel + 6 * b);
+#pragma unroll 1
         for (int s = 0; s < cnt; s++) {
           int c2 = s0 + s;
-          st3(sm + C::cpos + 3 * c2, cp_s[s]);
-          float pm = dist_s[s] - M.margin, imp = w_impedance(M, pm);
+          V3 cp = ld3(sm + C::cpos + 3 * c2);
+          float pm = sm[C::cD + c2] - M.margin, imp = w_impedance(M, pm);
           float R0 = fmaxf((1.f - imp) / imp * (M.tran_iw0[b] + M.mu * M.mu * M.tran_iw0[b]), 1e-15f);
           float R1 = R0 / fmaxf(M.impratio, 1e-15f), mu = M.mu * sqrtf(R1 / R0);
           sm[C::cD + c2] = 1.0f / (2.f * mu * mu * R0);
           float kterm = M.K * imp * pm;
-          for (int k = 0; k < 4; k++) sm[C::caref + 4 * c2 + k] = -M.B * dot6(w_wrench(M, cp_s[s], t1, k), v) - kterm;
+#pragma unroll 1
+          for (int k = 0; k < 4; k++) sm[C::caref + 4 * c2 + k] = -M.B * dot6(w_wrench(M, cp, t1, k), v) - kterm;
           // warmset: start from the working set this slot ended the previous substep with (new contacts: all rows active)
-          {
-            int inh = (M.warmset & 1) ? ((prevfl[s] & 1) ? (prevfl[s] & 30) : ((M.warmset & 2) ? 0 : 30)) : ((M.warmset & 4) ? 30 : 0);
-            cflag[c2] = M.warmset ? (1 | inh) : 1;
-          }
+          int pf = cflag[c2];
+          int inh = (M.warmset & 1) ? ((pf & 1) ? (pf & 30) : ((M.warmset & 2) ? 0 : 30)) : ((M.warmset & 4) ? 30 : 0);
+          cflag[c2] = M.warmset ? (1 | inh) : 1;
         }
         mask |= 1ull << (g + 1);
         nrows += 4 * cnt;
       }
+#pragma unroll 1
+      for (int s = s0 + cnt; s < s1; s++) cflag[s] = 0;
     }
     // joint limits (margin 0): compact list, at most W_MAXLIM rows (more would need >8 joints past +-range at once)
     for (int d = 6 + w.li; d < M.nv; d += C::LPE) {
@@ -745,6 +751,28 @@ __device__ __noinline__ void w_rows(const WModel<C>& M, float* sm, const WLane& 
   out4[0] = g1; out4[1] = g2; out4[2] = s1; out4[3] = s2;
 }
 
+// bodies whose articulated quantities depend on the working set: those carrying contact slots or limit rows, and their ancestors
+template <class C>
+__device__ __noinline__ unsigned long long w_dirty(const WModel<C>& M, const float* sm, const WLane& w, unsigned long long geom_mask) {
+  unsigned long long dm = 0ull;
+  if (w.live && w.li == 0) {
+    const int nlim = ((const int*)sm)[C::lim];
+#pragma unroll 1
+    for (int b = M.nb - 1; b > 0; b--) {
+      bool d = (dm >> b) & 1ull;
+      if (!d) {
+        for (int gi = M.bgeom_adr[b]; gi < M.bgeom_adr[b + 1]; gi++) d |= ((geom_mask >> (M.bgeom_list[gi] + 1)) & 1ull) != 0ull;
+        for (int e = 0; e < nlim; e++) { int dd = ((const int*)sm)[C::lim + 4 + 8 * e] - M.dofadr[b]; d |= (dd >= 0 && dd < M.dofnum[b]); }
+      }
+      if (d) dm |= (1ull << b) | (1ull << M.parent[b]);
+    }
+    dm |= 1ull;
+  }
+  int src = w.lane - w.li;
+  unsigned lo = __shfl_sync(W_FULL, (unsigned)(dm & 0xffffffffull), src), hi = __shfl_sync(W_FULL, (unsigned)(dm >> 32), src);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
 #ifdef SMPLSIM_TRACE
 __device__ float g_trace[8192];
 __device__ int g_trace_n;
@@ -755,7 +783,7 @@ __device__ int g_trace_n;
 #endif
 // ------------------------------------------------------------------ constraint solve (active-set Newton, each system one ABA); returns extra solves
 template <class C>
-__device__ __noinline__ int w_solve(const WModel<C>& M, float* sm, const WLane& w, bool any_rows) {
+__device__ __noinline__ int w_solve(const WModel<C>& M, float* sm, const WLane& w, bool any_rows, unsigned long long geom_mask) {
   bool plain = w.live && !any_rows;
   if (__any_sync(W_FULL, plain)) {
     w_inward(M, sm, w, plain, W_INERTIA | W_FORCE | W_PB, 0, 0);
@@ -770,9 +798,11 @@ __device__ __noinline__ int w_solve(const WModel<C>& M, float* sm, const WLane& 
   bool have_point = false;
   int it = 0, iters = 0;
   float o4[4];
+  unsigned long long dirty = 0ull;
   for (; it < W_SOLVER_MAXITER; it++) {
     if (!__any_sync(W_FULL, run)) break;
-    w_inward(M, sm, w, run, W_INERTIA | W_FORCE | W_PB | W_CONTACTS, 0, 0);
+    if (it == 1 && M.dirtypath) dirty = w_dirty(M, sm, w, geom_mask);
+    w_inward(M, sm, w, run, W_INERTIA | W_FORCE | W_PB | W_CONTACTS, 0, 0, dirty);
     w_outward(M, sm, w, run, 1, 0);
     bool same = w_eval_rows(M, sm, w, run, 1);
     bool fin = run && same, adopt = run && !same && !have_point, lsrch = run && !same && have_point;
@@ -968,17 +998,23 @@ __device__ __noinline__ int w_check(const WModel<C>& M, float* sm, const WLane& 
   bool b0 = false, b1 = false;
   if (w.live) {
     if (what == 0) {
+#pragma unroll 1
       for (int i = w.li; i < M.nv + 1; i += C::LPE) b0 |= !(fabsf(sm[C::qpos + i]) <= W_MAXVAL);
+#pragma unroll 1
       for (int i = w.li; i < M.nv; i += C::LPE) b1 |= !(fabsf(sm[C::qvel + i]) <= W_MAXVAL);
     } else {
+#pragma unroll 1
       for (int i = w.li; i < M.nv; i += C::LPE) b0 |= !(fabsf(sm[C::qacc + i]) <= W_MAXVAL);
     }
   }
   b0 = w_gany(b0, w); b1 = w_gany(b1, w);
   int bits = (what == 0) ? (b0 ? 1 : (b1 ? 2 : 0)) : (b0 ? 4 : 0);
   if (bits && w.live) {
+#pragma unroll 1
     for (int i = w.li; i < M.nv + 1; i += C::LPE) sm[C::qpos + i] = (i < 3) ? M.bpos[0][i] : (i < 7) ? M.bquat[0][i - 3] : 0.f;
+#pragma unroll 1
     for (int i = w.li; i < M.nv; i += C::LPE) { sm[C::qvel + i] = 0.f; sm[C::qacc + i] = 0.f; }
+#pragma unroll 1
     for (int i = w.li; i < M.nu; i += C::LPE) sm[C::tau + i] = 0.f;
   }
   __syncwarp();
@@ -996,7 +1032,14 @@ __device__ __noinline__ float w_substeps(const WModel<C>& M, float* sm, const WL
   for (int s = 0; s < nsub; s++) {
     // keep the warps of a CTA in the same phase: the hot code of one phase fits the instruction cache, that of
     // 14 drifting warps does not (round-1 profile: "no_instruction" was the top stall)
-    if (align > 0 && (s % align) == 0) __syncthreads();
+    if ((align & 255) > 0 && (s % (align & 255)) == 0) {
+      const int G = align >> 8;              // warps per barrier group (0: the whole CTA)
+      if (G == 0) __syncthreads();
+      else {
+        int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5, grp = wib / G, cnt = min(G, wpb - grp * G) * 32;
+        asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(cnt) : "memory");
+      }
+    }
     bool did_fk = false;
     if (!raw) {
       if (spd && !stale) { w_fk(M, sm, w, true); w_spd_prepare(M, sm, w); did_fk = true; }
@@ -1014,7 +1057,7 @@ __device__ __noinline__ float w_substeps(const WModel<C>& M, float* sm, const WL
     unsigned lo = w_gor<C>((unsigned)(m & 0xffffffffull)), hi = w_gor<C>((unsigned)(m >> 32));
     fo->mask = ((unsigned long long)hi << 32) | lo;
     bool any_rows = w_gany(w.live && nrows > 0, w);
-    fo->iters = w_solve(M, sm, w, any_rows);
+    fo->iters = w_solve(M, sm, w, any_rows, fo->mask);
     int badacc = w_check(M, sm, w, 1);
     if (__any_sync(W_FULL, badacc != 0)) {   // mj_checkAcc: forward pass again on the reset data, then integrate
       WLane w2 = w;
@@ -1024,7 +1067,7 @@ __device__ __noinline__ float w_substeps(const WModel<C>& M, float* sm, const WL
       unsigned long long m2 = w_collide(M, sm, w2, &nrows2);
       unsigned lo2 = w_gor<C>((unsigned)(m2 & 0xffffffffull)), hi2 = w_gor<C>((unsigned)(m2 >> 32));
       bool any2 = w_gany(w2.live && nrows2 > 0, w2);
-      int it2 = w_solve(M, sm, w2, any2);
+      int it2 = w_solve(M, sm, w2, any2, ((unsigned long long)hi2 << 32) | lo2);
       if (badacc) { fo->mask = ((unsigned long long)hi2 << 32) | lo2; fo->iters = it2; }
     }
     bad |= badacc;
