@@ -754,23 +754,24 @@ __device__ __noinline__ void w_rows(const WModel<C>& M, float* sm, const WLane& 
 // bodies whose articulated quantities depend on the working set: those carrying contact slots or limit rows, and their ancestors
 template <class C>
 __device__ __noinline__ unsigned long long w_dirty(const WModel<C>& M, const float* sm, const WLane& w, unsigned long long geom_mask) {
-  unsigned long long dm = 0ull;
-  if (w.live && w.li == 0) {
-    const int nlim = ((const int*)sm)[C::lim];
+  // own bit per body (lane-parallel, ballot), then ancestor closure (bodies are in topological order: parent < child)
+  const int nlim = w.live ? ((const int*)sm)[C::lim] : 0;
+  unsigned long long dm = 1ull;
 #pragma unroll 1
-    for (int b = M.nb - 1; b > 0; b--) {
-      bool d = (dm >> b) & 1ull;
-      if (!d) {
-        for (int gi = M.bgeom_adr[b]; gi < M.bgeom_adr[b + 1]; gi++) d |= ((geom_mask >> (M.bgeom_list[gi] + 1)) & 1ull) != 0ull;
-        for (int e = 0; e < nlim; e++) { int dd = ((const int*)sm)[C::lim + 4 + 8 * e] - M.dofadr[b]; d |= (dd >= 0 && dd < M.dofnum[b]); }
-      }
-      if (d) dm |= (1ull << b) | (1ull << M.parent[b]);
+  for (int b0 = 0; b0 < M.nb; b0 += C::LPE) {
+    int b = b0 + w.li;
+    bool d = false;
+    if (w.live && b > 0 && b < M.nb) {
+      for (int gi = M.bgeom_adr[b]; gi < M.bgeom_adr[b + 1]; gi++) d |= ((geom_mask >> (M.bgeom_list[gi] + 1)) & 1ull) != 0ull;
+      for (int e = 0; e < nlim; e++) { int dd = ((const int*)sm)[C::lim + 4 + 8 * e] - M.dofadr[b]; d |= (dd >= 0 && dd < M.dofnum[b]); }
     }
-    dm |= 1ull;
+    unsigned bal = (__ballot_sync(W_FULL, d) & w.gmask) >> (w.lane - w.li);
+    dm |= (unsigned long long)bal << b0;
   }
-  int src = w.lane - w.li;
-  unsigned lo = __shfl_sync(W_FULL, (unsigned)(dm & 0xffffffffull), src), hi = __shfl_sync(W_FULL, (unsigned)(dm >> 32), src);
-  return ((unsigned long long)hi << 32) | lo;
+#pragma unroll 1
+  for (int b = M.nb - 1; b > 0; b--)
+    if ((dm >> b) & 1ull) dm |= 1ull << M.parent[b];
+  return dm;
 }
 
 #ifdef SMPLSIM_TRACE
