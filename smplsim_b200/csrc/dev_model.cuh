@@ -41,6 +41,7 @@ struct DevModel {
   int obs_dim, self_obs_dim;
   int rowpar;                           // 1: row-parallel sweeps (8 lanes per body) when LPE == 32
   int warmset;                          // 1: solver starts from the previous substep's working set per contact slot
+  float ls_tol;                         // line-search stop: |derivative| <= ls_tol * |derivative at 0|
   int dirtypath;                        // 1: solver iterations >= 2 re-sweep only the bodies on paths from constraint rows to the root
   int sched_T, sched[SM_MAXSCHED][4];   // 4-slot list schedule of the inward sweep (row-parallel kernels); sched_T = 0: none
   int sched_nd[SM_MAXSCHED], sched_nc[SM_MAXSCHED], sched_ns[SM_MAXSCHED];  // per step: max dofs / children / contact slots (uniform loop bounds)

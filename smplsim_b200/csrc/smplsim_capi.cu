@@ -257,6 +257,7 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
     const char* ws = std::getenv("SMPLSIM_WARMSET");
     m.warmset = ws ? std::atoi(ws) : 1;
     { const char* dp = std::getenv("SMPLSIM_DIRTYPATH"); m.dirtypath = dp ? std::atoi(dp) : 1; }
+    { const char* lt = std::getenv("SMPLSIM_LS_TOL"); m.ls_tol = lt ? (float)std::atof(lt) : 1e-6f; }
     const char* rp = std::getenv("SMPLSIM_ROWS");
     m.rowpar = rp ? std::atoi(rp) : 0;   // opt-in: measured slower than the level sweeps in round 1 (profiles/r1_k_step3_rows.md)
   }

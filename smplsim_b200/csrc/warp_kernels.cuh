@@ -43,6 +43,7 @@ struct WCfg {
 template <class C>
 struct WModel {
   int nb, nv, nu, ng, nlevel, nslot, sched_T, rowpar, warmset, dirtypath;
+  float ls_tol;
   int sched[SM_MAXSCHED][4], sched_nd[SM_MAXSCHED], sched_nc[SM_MAXSCHED], sched_ns[SM_MAXSCHED];
   int parent[C::NB], dofadr[C::NB], dofnum[C::NB];
   int level_adr[SM_MAXL + 1], level_list[C::NB], child_adr[C::NB + 1], child_list[C::NB];
@@ -68,7 +69,7 @@ __device__ void w_stage_model(const DevModel* __restrict__ G, WModel<C>& M) {
     for (int i = 0; i < 5; i++) M.solimp[i] = G->solimp[i];
     M.imp_a = G->imp_a; M.imp_b = G->imp_b; M.K = G->K; M.B = G->B; M.h = G->h; M.legal_mask = G->legal_mask; M.cfg = G->cfg;
     M.obs_dim = G->obs_dim; M.self_obs_dim = G->self_obs_dim;
-    M.sched_T = G->sched_T; M.rowpar = G->rowpar; M.warmset = G->warmset; M.dirtypath = G->dirtypath;
+    M.sched_T = G->sched_T; M.rowpar = G->rowpar; M.warmset = G->warmset; M.dirtypath = G->dirtypath; M.ls_tol = G->ls_tol;
     for (int i = 0; i < SM_MAXSCHED; i++) {
       for (int k = 0; k < 4; k++) M.sched[i][k] = G->sched[i][k];
       M.sched_nd[i] = G->sched_nd[i]; M.sched_nc[i] = G->sched_nc[i]; M.sched_ns[i] = G->sched_ns[i];
@@ -815,7 +816,7 @@ __device__ __noinline__ int w_solve(const WModel<C>& M, float* sm, const WLane& 
     if (__any_sync(W_FULL, lsrch)) {   // exact line search between the iterate (qacc, acc2) and the trial point (qstar, acc), row space only
       w_rows(M, sm, w, lsrch, 1, 0.f, o4);
       float g1 = w_gsum<C>(o4[0]), g2 = w_gsum<C>(o4[1]), s1 = w_gsum<C>(o4[2]), s2;
-      float f0 = g1 + s1, al = 0.f, lo = 0.f, hi = -1.f, tol = 1e-6f * fabsf(f0);
+      float f0 = g1 + s1, al = 0.f, lo = 0.f, hi = -1.f, tol = M.ls_tol * fabsf(f0);
       bool searching = lsrch && (f0 < -W_LS_NOISE * (fabsf(g1) + fabsf(s1)));   // |f0| below the fp32 cancellation floor: converged
       if (searching) al = 1.f;
       for (int ls = 0; ls < W_LS_MAXITER; ls++) {
