@@ -39,6 +39,8 @@ extern "C" {
 #define SMPLSIM_CTRL_UHC_PD 0 /* StablePDController    smpl_sim/envs/controllers.py:50-190 */
 #define SMPLSIM_CTRL_PD 1     /* PIDController (ki=0)  smpl_sim/envs/controllers.py:265-349 */
 #define SMPLSIM_CTRL_TORQUE 2 /* SimpleTorqueController smpl_sim/envs/controllers.py:6-47 */
+#define SMPLSIM_CTRL_SIMPLE_PID 3 /* SimplePID (stateful) smpl_sim/envs/controllers.py:186-262, built at humanoid_env.py:318-319:
+                                   * act_kp = jkp/10, act_kd = jkd/10, Ki = 1, dt = timestep * control_freq_inv */
 
 #define SMPLSIM_INIT_DEFAULT 0 /* humanoid_env.py:472-477 */
 #define SMPLSIM_INIT_FALL 1    /* humanoid_env.py:478-491 */
@@ -119,6 +121,9 @@ typedef struct SmplsimState {
   int32_t* progress;        /* [N]  cur_t */
   int32_t* recovery;        /* [N]  getup recovery counter */
   uint32_t* rng_counter;    /* [N]  Philox counter */
+  float* pid_integral;      /* [N,nu] SimplePID._integral   (control_mode simple_pid only, else may be NULL); like the reference's
+                             *        controller object it is NOT cleared by reset */
+  float* pid_last_error;    /* [N,nu] SimplePID._last_error ; NaN = None (first call: d_error = 0) */
 } SmplsimState;
 
 /* Side outputs of the last forward pass / kinematics (any pointer may be NULL). */

@@ -50,7 +50,7 @@ def lib():
         L.orc_env_step.argtypes = [C.c_void_p, C.c_void_p, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_env_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, dp, dp, dp]
         for f in ("qpos", "qvel", "ctrl", "qacc", "qacc_warm", "qacc_smooth", "qfrc_bias", "qfrc_constraint", "M", "xpos",
-                  "xquat", "sensor", "target", "last_torque", "con_dist", "con_pos", "con_frame", "efc_force",
+                  "xquat", "sensor", "target", "last_torque", "pid_integral", "pid_last_error", "con_dist", "con_pos", "con_frame", "efc_force",
                   "efc_aref", "efc_D", "efc_J", "sub_com"):
             fn = getattr(L, "orc_" + f)
             fn.restype = dp
@@ -118,6 +118,7 @@ class OracleEnv:
         self.sensor = view("sensor", (2, nb, 3))
         self.target = view("target", (4,))
         self.last_torque = view("last_torque", (nu,))
+        self.pid_integral, self.pid_last_error = view("pid_integral", (nu,)), view("pid_last_error", (nu,))
         self.sub_com = view("sub_com", (3,))
         self._con_dist = view("con_dist", (256,))
         self._con_pos = view("con_pos", (256, 3))

@@ -7,7 +7,7 @@ from typing import Any
 from .model import ModelDesc, SmplsimModelDescC  # noqa: F401
 
 TASKS = {"HumanoidEnv": 0, "HumanoidSpeed": 1, "HumanoidReach": 2, "HumanoidGetup": 3}
-CTRL_MODES = {"uhc_pd": 0, "pd": 1, "torque": 2}
+CTRL_MODES = {"uhc_pd": 0, "pd": 1, "torque": 2, "simple_pid": 3}
 STATE_INITS = {"Default": 0, "Fall": 1, "MoCap": 2}
 _AVAILABLE_CONTROLLERS = ["uhc_pd", "simple_pid", "pd", "torque", "default"]   # humanoid_env.py:32
 
@@ -29,6 +29,7 @@ class SmplsimStateC(C.Structure):
         ("qpos", C.c_void_p), ("qvel", C.c_void_p), ("qpos_fwd", C.c_void_p), ("qvel_fwd", C.c_void_p),
         ("qacc_warm", C.c_void_p), ("task_target", C.c_void_p), ("task_change_step", C.c_void_p),
         ("progress", C.c_void_p), ("recovery", C.c_void_p), ("rng_counter", C.c_void_p),
+        ("pid_integral", C.c_void_p), ("pid_last_error", C.c_void_p),
     ]
 
 

@@ -64,6 +64,8 @@ class HumanoidBatchB200:
         self.progress_buf = torch.zeros(N, **i32)
         self.recovery = torch.zeros(N, **i32)
         self.rng_counter = torch.zeros(N, **i32)
+        self.pid_integral = torch.zeros(N, m.nu, **f32)              # SimplePID state (simple_pid only; survives reset, like the reference object)
+        self.pid_last_error = torch.full((N, m.nu), float('nan'), **f32)   # NaN = None
         self.obs_buf = torch.zeros(N, self.num_obs, **f32)
         self.rew_buf = torch.zeros(N, **f32)
         self.terminate_buf = torch.zeros(N, dtype=torch.uint8, device=dv)
@@ -82,7 +84,7 @@ class HumanoidBatchB200:
         self.extras = {"terminate": self.terminate_buf, "sim_warning": self.status}
         self._state = SmplsimStateC(*[t.data_ptr() for t in (self.qpos, self.qvel, self.qpos_fwd, self.qvel_fwd, self.qacc_warm,
                                                              self.task_target, self.task_change_step, self.progress_buf,
-                                                             self.recovery, self.rng_counter)])
+                                                             self.recovery, self.rng_counter, self.pid_integral, self.pid_last_error)])
         self._aux = SmplsimAuxC(*[t.data_ptr() for t in (self.xpos, self.xquat, self.body_linvel, self.body_angvel,
                                                          self.contact_mask, self.qacc, self.ctrl, self.solver_iter, self.status)])
         if not with_aux:        # throughput runs: skip the side outputs (NULL pointers), keep the 1-byte status

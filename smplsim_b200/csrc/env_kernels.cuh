@@ -115,7 +115,7 @@ __device__ float run_substeps(const DevModel& M, const EnvLayout& L, float* sm, 
     bool did_fk = false;
     if (!raw) {
       if (spd && !stale) { fk_pass<true>(M, L, sm, lane); spd_prepare(M, L, sm, lane); did_fk = true; }
-      compute_torque(M, L, sm, lane);
+      compute_torque(M, L, sm, lane, st, env);
     } else if (restore) {
       for (int i = lane; i < M.nu; i += 32) sm[L.tau + i] = sm[L.act + i];
       restore = false;

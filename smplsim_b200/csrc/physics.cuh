@@ -576,12 +576,25 @@ __device__ void spd_prepare(const DevModel& M, const EnvLayout& L, float* sm, in
 }
 
 // torque for this substep from action `act` (controllers.py:116-163 | 316-346 | 26-47) -> tau
-__device__ void compute_torque(const DevModel& M, const EnvLayout& L, float* sm, int lane) {
+__device__ void compute_torque(const DevModel& M, const EnvLayout& L, float* sm, int lane, const SmplsimState& st, int env) {
   const float *qpos = sm + L.qpos, *qvel = sm + L.qvel, *act = sm + L.act;
   float *tau = sm + L.tau, *tin = sm + L.tin;
   int mode = M.cfg.control_mode;
   if (mode == SMPLSIM_CTRL_TORQUE) {
     for (int i = lane; i < M.nu; i += 32) tau[i] = fminf(fmaxf(act[i] * M.ascale[i], -M.tlim[i]), M.tlim[i]);
+    __syncwarp();
+    return;
+  }
+  if (mode == SMPLSIM_CTRL_SIMPLE_PID) {
+    float dt = M.h * (float)M.cfg.nsubsteps;
+    for (int i = lane; i < M.nu; i += 32) {
+      size_t o = (size_t)env * M.nu + i;
+      float lim = M.tlim[i], err = fmaf(act[i], M.ascale[i], M.aoffset[i]) - qpos[7 + i], le = st.pid_last_error[o];
+      float derr = (le != le) ? 0.f : err - le;
+      float in = fminf(fmaxf(fmaf(err, dt, st.pid_integral[o]), -lim), lim);
+      st.pid_integral[o] = in; st.pid_last_error[o] = err;
+      tau[i] = fminf(fmaxf(M.kp[i] * err + in + M.kd[i] * derr / dt, -lim), lim);
+    }
     __syncwarp();
     return;
   }

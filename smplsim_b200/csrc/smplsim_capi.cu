@@ -153,7 +153,7 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   if (s->nq != s->nv + 1 || s->nu != s->nv - 6 || s->body_dofnum[0] != 6 || s->body_parent[0] != -1)
     return fail(SMPLSIM_EUNSUPPORTED, "model class: one tree rooted at a free joint, hinge joints elsewhere");
   if (cfg->self_obs_v != 1 && cfg->self_obs_v != 2) return fail(SMPLSIM_EINVAL, "self_obs_v must be 1 or 2");
-  if (cfg->control_mode < 0 || cfg->control_mode > 2) return fail(SMPLSIM_EINVAL, "control_mode must be uhc_pd|pd|torque");
+  if (cfg->control_mode < 0 || cfg->control_mode > 3) return fail(SMPLSIM_EINVAL, "control_mode must be uhc_pd|pd|torque|simple_pid");
   if (cfg->task < 0 || cfg->task > 3) return fail(SMPLSIM_EINVAL, "unknown task");
   if (cfg->nsubsteps < 1) return fail(SMPLSIM_EINVAL, "nsubsteps < 1");
   SmplsimHandle* h = new SmplsimHandle();
@@ -283,6 +283,7 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
     ChainPlan P = chain_plan(s, CH_MAXLEDGE);
     if (!P.ok) h->v2_why = P.why;
     else if (P.T > 16) h->v2_why = "schedule longer than 16 steps";
+    else if (cfg->control_mode == SMPLSIM_CTRL_SIMPLE_PID) h->v2_why = "simple_pid is only built for the v1 / v3 kernels";
     else if (!force || std::string(force) != "v2") h->v2_why = "chain-lane kernels are opt-in (SMPLSIM_KERNEL=v2)";
     else {
       ChainConsts& k = h->kc;
@@ -315,6 +316,7 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
     ChainPlan P = chain_plan(s, 0, false);
     if (!want) h->v4_why = "not selected";
     else if (h->v2) h->v4_why = "v2 forced";
+    else if (cfg->control_mode == SMPLSIM_CTRL_SIMPLE_PID) h->v4_why = "simple_pid is only built for the v1 / v3 kernels";
     else if (!P.ok) h->v4_why = P.why;
     else if (P.T > TPE_MAXT) h->v4_why = "schedule longer than 16 steps";
     else if (m.nb != TC_SMPL::NB || m.nv != TC_SMPL::NV) h->v4_why = "model size is not the SMPL class (24 bodies, 75 dofs)";

@@ -870,13 +870,21 @@ __device__ __noinline__ void w_spd_prepare(const WModel<C>& M, float* sm, const 
 }
 
 template <class C>
-__device__ __noinline__ void w_torque(const WModel<C>& M, float* sm, const WLane& w) {
+__device__ __noinline__ void w_torque(const WModel<C>& M, float* sm, const WLane& w, const SmplsimState& st, int env) {
   int mode = M.cfg.control_mode;
   if (w.live) {
     for (int i = w.li; i < M.nu; i += C::LPE) {
       float a = sm[C::act + i], tq;
       if (mode == SMPLSIM_CTRL_TORQUE) tq = a * M.ascale[i];
-      else {
+      else if (mode == SMPLSIM_CTRL_SIMPLE_PID) {   // stateful: integral / last error live in HBM (L2-resident, 2 x nu words per env)
+        size_t o = (size_t)env * M.nu + i;
+        float dt = M.h * (float)M.cfg.nsubsteps, lim = M.tlim[i];
+        float err = fmaf(a, M.ascale[i], M.aoffset[i]) - sm[C::qpos + 7 + i], le = st.pid_last_error[o];
+        float derr = (le != le) ? 0.f : err - le;
+        float in = fminf(fmaxf(fmaf(err, dt, st.pid_integral[o]), -lim), lim);
+        st.pid_integral[o] = in; st.pid_last_error[o] = err;
+        tq = M.kp[i] * err + in + M.kd[i] * derr / dt;
+      } else {
         float tgt = fmaf(a, M.ascale[i], M.aoffset[i]), q = sm[C::qpos + 7 + i], qd = sm[C::qvel + 6 + i];
         if (mode == SMPLSIM_CTRL_PD) tq = -M.kp[i] * (q - tgt) - M.kd[i] * qd;
         else tq = -M.kp[i] * (q + qd * M.h - tgt) - M.kd[i] * (qd + sm[C::spdab + 6 + i] * M.h);
@@ -1045,7 +1053,7 @@ __device__ __noinline__ float w_substeps(const WModel<C>& M, float* sm, const WL
     bool did_fk = false;
     if (!raw) {
       if (spd && !stale) { w_fk(M, sm, w, true); w_spd_prepare(M, sm, w); did_fk = true; }
-      w_torque(M, sm, w);
+      w_torque(M, sm, w, st, env);
     } else if (__any_sync(W_FULL, restore)) {
       if (w.live && restore) for (int i = w.li; i < M.nu; i += C::LPE) sm[C::tau + i] = sm[C::act + i];
       restore = false;

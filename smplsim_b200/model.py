@@ -367,6 +367,10 @@ def build_model(p: ParsedMJCF, *, timestep: float = 1.0 / 450.0, contact_bodies:
     if control_mode in ("pd", "uhc_pd"):
         kp = kp / pdp_scale
         kd = kd / pdd_scale
+    if control_mode == "simple_pid":
+        # SimplePID(self.jkp/10, ones, self.jkd/10, timestep*control_freq_inv, torque_lim, ...): humanoid_env.py:318-319
+        kp = kp / 10.0
+        kd = kd / 10.0
     if control_mode == "torque":
         # SimpleTorqueController(power_scale * torque_lim, torque_lim): humanoid_env.py:321.
         # (the reference leaves torque_lim at zero in this mode -- build_pd_action_scale only

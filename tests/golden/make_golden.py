@@ -227,6 +227,39 @@ def gen_controllers(seed=7, B=12):
           float(np.mean(np.abs(out["torque_spd"]) >= f.torque_lim[None] - 1e-9)))
 
 
+def gen_simple_pid(seed=11, T=40):
+    """SimplePID (controllers.py:186-262) as humanoid_env.setup_controller builds it (:318-319): Kp = jkp/10, Ki = 1, Kd = jkd/10,
+    dt = timestep * control_freq_inv, stateful (integral, last error) across calls -- a T-call sequence on one controller."""
+    rng = np.random.default_rng(seed)
+    m = load_model("smpl")
+    nu = m.nu
+
+    class FakeJoint:
+        def __init__(self, r):
+            self.range = r
+
+    class FakeModel:
+        def joint(self, n):
+            return FakeJoint(m.dof_range[6 + m.joint_names.index(n)])
+
+    fake = types.SimpleNamespace(dof_size=nu, actuator_names=list(m.joint_names), mj_model=FakeModel(), control_mode="simple_pid", clip_actions=True)
+    HE.HumanoidEnv.build_pd_action_scale(fake)
+    dt = (1.0 / 450.0) * 15
+    ctl = CT.SimplePID(fake.jkp / 10, np.ones_like(fake.jkp), fake.jkd / 10, dt, fake.torque_lim, fake._pd_action_scale, fake._pd_action_offset)
+    q = rng.uniform(-0.5, 0.5, nu)
+    qs, acts, taus = [], [], []
+    for t in range(T):
+        if t % 5 == 0:
+            a = np.clip(rng.normal(size=nu) * 0.3, -1, 1)
+        q = q + rng.normal(size=nu) * 0.01
+        qpos = np.zeros(m.nq); qpos[7:] = q
+        tau = ctl.control(a, None, types.SimpleNamespace(qpos=qpos))
+        qs.append(qpos.copy()); acts.append(a.copy()); taus.append(np.array(tau).copy())
+    np.savez_compressed(os.path.join(HERE, "simple_pid_smpl.npz"), qpos=np.array(qs), action=np.array(acts), torque=np.array(taus), dt=dt,
+                        jkp=fake.jkp, jkd=fake.jkd, torque_lim=fake.torque_lim)
+    print("simple_pid_smpl.npz: |tau| max", np.abs(np.array(taus)).max(), "clipped frac", float(np.mean(np.abs(np.array(taus)) >= fake.torque_lim[None] - 1e-9)))
+
+
 def gen_frame_blend(seed=3, B=256):
     """MotionLibBase._calc_frame_blend + the frame index expression of get_motion_state_intervaled
     (motion_lib_base.py:321-323,448-458) -- executed from the reference source text, since importing the
@@ -278,4 +311,5 @@ if __name__ == "__main__":
     gen_obs("smpl", 24, 69, seed=11)
     gen_obs("smplx", 52, 153, seed=12, B=8)
     gen_controllers()
+    gen_simple_pid()
     gen_frame_blend()

@@ -414,3 +414,28 @@ def test_bad_state_autoreset_matches_mj_step_semantics(case):
     ref = env.qpos[0].cpu().numpy()
     for i in (1, 2, 4, 5, 6, 7):                            # neighbours in the same CTA are untouched
         assert np.array_equal(env.qpos[i].cpu().numpy(), ref)
+
+
+def test_env_step_simple_pid_matches_oracle():
+    """control_mode simple_pid: the stateful SimplePID (integral / last error carried across substeps, steps and resets)."""
+    cfg, om = make_models(env="speed", control_mode="simple_pid", seed=5)
+    m = om.model
+    n = 8
+    env = _batch(cfg, n, seed=5)
+    env.reset()
+    oes = [orc.OracleEnv(om, env_id=i) for i in range(n)]
+    for e in oes:
+        e.reset()
+    rng = np.random.default_rng(2)
+    for t in range(3):
+        act = np.clip(rng.normal(size=(n, m.nu)) * 0.1, -1, 1)
+        obs, rew, term, trunc = [x.cpu().numpy() for x in env.step(_t(act))]
+        gi, gl = env.pid_integral.cpu().numpy(), env.pid_last_error.cpu().numpy()
+        for i, e in enumerate(oes):
+            o, r, te, tr = e.step(act[i])
+            tol = 1e-3 * (t + 1)
+            assert relerr(obs[i], o) < tol, (t, i, relerr(obs[i], o))       # obs carries joint velocities of ~40 rad/s here
+            assert relerr(gi[i], e.pid_integral) < tol and relerr(gl[i], e.pid_last_error) < tol
+            assert bool(term[i]) == te and bool(trunc[i]) == tr
+    env.reset()                                   # the controller state survives reset, as the reference's controller object does
+    assert env.pid_integral.abs().max() > 0 and torch.isfinite(env.pid_last_error).all()

@@ -129,3 +129,18 @@ def test_oracle_bad_state_autoreset():
     e.reset(); e.warn = 0
     e.step(np.zeros(m.nu))
     assert e.warn == 0
+
+
+def test_simple_pid_matches_reference_sequence():
+    """SimplePID (controllers.py:186-262; Kp = jkp/10, Ki = 1, Kd = jkd/10, dt = 15/450) -- a stateful 40-call sequence generated by
+    the reference's own class (tests/golden/make_golden.py:gen_simple_pid)."""
+    g = np.load(os.path.join(GOLDEN, "simple_pid_smpl.npz"))
+    cfg = make_cfg(env="speed", overrides={"env.control_mode": "simple_pid"})
+    om = orc.OracleModel.from_cfg(cfg)
+    m = om.model
+    assert np.allclose(m.act_kp, g["jkp"] / 10) and np.allclose(m.act_kd, g["jkd"] / 10) and np.allclose(m.act_torque_lim, g["torque_lim"])
+    e = orc.OracleEnv(om)
+    for t in range(g["qpos"].shape[0]):
+        e.qpos[:] = g["qpos"][t]
+        tau = e.compute_torque(g["action"][t])
+        assert np.abs(tau - g["torque"][t]).max() < 1e-9, t
