@@ -7,7 +7,7 @@ from typing import Any
 from .model import ModelDesc, SmplsimModelDescC  # noqa: F401
 
 TASKS = {"HumanoidEnv": 0, "HumanoidSpeed": 1, "HumanoidReach": 2, "HumanoidGetup": 3}
-CTRL_MODES = {"uhc_pd": 0, "pd": 1, "torque": 2, "simple_pid": 3}
+CTRL_MODES = {"uhc_pd": 0, "pd": 1, "torque": 2, "simple_pid": 3, "default": 2}   # "default": ctrl = action (humanoid_env.py:409-410) = torque mode, scale 1, no limit
 STATE_INITS = {"Default": 0, "Fall": 1, "MoCap": 2}
 _AVAILABLE_CONTROLLERS = ["uhc_pd", "simple_pid", "pd", "torque", "default"]   # humanoid_env.py:32
 

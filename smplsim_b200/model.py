@@ -378,6 +378,12 @@ def build_model(p: ParsedMJCF, *, timestep: float = 1.0 / 450.0, contact_bodies:
         scale = power_scale * tl
         offset = np.zeros(nu)
 
+    if control_mode == "default":
+        # compute_torque returns the action itself (humanoid_env.py:407-410): torque mode with unit scale and no clipping
+        scale = np.ones(nu)
+        offset = np.zeros(nu)
+        tl = np.full(nu, 3.0e38)
+
     zaxis = p.floor.mat[:, 2]
     qpos0 = np.zeros(nv + 1)
     qpos0[0:3] = p.bodies[0].pos

@@ -155,3 +155,28 @@ def test_batched_sampler_shapes_and_masks():
     assert torch.equal(b["states"][6, :, 0], torch.full((n,), 0.94, device="cuda:0"))   # next state after the in-stream reset
     adv, ret = estimate_advantages(b["rewards"], b["not_done"], b["not_dead"], torch.zeros(T, n, device="cuda:0"), 0.99, 0.95)
     assert torch.isfinite(adv).all() and abs(adv.mean().item()) < 1e-4 and abs(adv.std().item() - 1) < 1e-3
+
+
+def test_two_ppo_epochs_getup_plumbing():
+    """BASELINE config 1 as a plumbing check: env=getup, two PPO epochs (sample -> GAE -> update) complete through the
+    batched surface with obs / action shapes (290,) / (69,) and finite losses; the policy parameters move."""
+    from smplsim_b200.batched import HumanoidBatchB200
+    from smplsim_b200.learning import BatchedSampler
+    from smplsim_b200.ppo import PolicyGaussian, PPOLearner, Value
+    env = HumanoidBatchB200(make_cfg(env="getup"), num_envs=64, seed=1)
+    assert env.num_obs == 290 and env.num_actions == 69
+    torch.manual_seed(0)
+    policy = PolicyGaussian(290, 69, [64, 32]).to("cuda:0")
+    value = Value(290, [64, 32]).to("cuda:0")
+    learner = PPOLearner(policy, value, opt_num_epochs=2)
+    w0 = policy.action_mean.weight.detach().clone()
+
+    def act(o):
+        policy.eval()
+        return policy.select_action(o)
+
+    sampler = BatchedSampler(env, act)
+    for _ in range(2):
+        info = learner.update(sampler.sample(6))
+        assert all(np.isfinite(v) for v in info.values()), info
+    assert int(policy.norm.n) == 2 * 2 * 6 * 64 and not torch.equal(w0, policy.action_mean.weight)

@@ -144,3 +144,12 @@ def test_simple_pid_matches_reference_sequence():
         e.qpos[:] = g["qpos"][t]
         tau = e.compute_torque(g["action"][t])
         assert np.abs(tau - g["torque"][t]).max() < 1e-9, t
+
+
+def test_default_control_mode_passes_action_through():
+    """control_mode "default": compute_torque returns ctrl unchanged (humanoid_env.py:407-410)."""
+    cfg = make_cfg(env="speed", overrides={"env.control_mode": "default"})
+    om = orc.OracleModel.from_cfg(cfg)
+    e = orc.OracleEnv(om)
+    a = np.linspace(-700.0, 900.0, om.model.nu)
+    assert np.array_equal(e.compute_torque(a), a)
