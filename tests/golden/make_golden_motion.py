@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Generate tests/golden/motion_fk.npz with the REFERENCE's Humanoid_Batch.fk_batch (smpl_sim/smpllib/torch_smpl_humanoid_batch.py:118-228:
+SMPL axis-angle pose -> MuJoCo-ordered qpos/qvel, global body transforms, finite-difference + gaussian velocities).  The class
+ctor needs the SMPL model files, so the unbound methods run on a namespace carrying what they read: `_offsets` (the shipped XML's
+body offsets, rounded to 5 decimals like update_model does, :113), `_parents`, `smpl_2_mujoco`, `dt`, `filter_vel`."""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden as MG  # noqa: E402
+
+HB = MG._import_with_stubs(lambda: __import__("smpl_sim.smpllib.torch_smpl_humanoid_batch", fromlist=["x"]))
+from smpl_sim.smpllib.smpl_joint_names import SMPL_BONE_ORDER_NAMES, SMPL_MUJOCO_NAMES  # noqa: E402
+from smplsim_b200.model import load_model  # noqa: E402
+
+
+class _Dict(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+def main():
+    HB.EasyDict = _Dict
+    m = load_model("smpl")
+    assert list(m.body_names) == list(SMPL_MUJOCO_NAMES)
+    rng = np.random.default_rng(8)
+    F, fps = 48, 30
+    # smooth random motion: per-joint sinusoids in axis-angle (SMPL joint order), walking root
+    t = np.arange(F) / fps
+    amp = rng.uniform(0.0, 0.5, (24, 3)); frq = rng.uniform(0.3, 1.5, (24, 3)); ph = rng.uniform(0, 6.28, (24, 3))
+    pose_aa = amp[None] * np.sin(2 * np.pi * frq[None] * t[:, None, None] + ph[None])
+    pose_aa[:, 0] = np.array([1.2, 1.2, 1.2])[None] + 0.2 * np.sin(2 * np.pi * 0.5 * t)[:, None]   # root near the upright-start rotation
+    pose_aa[:, 16, 2] += 2.0 * np.sin(2 * np.pi * 0.7 * t)          # one large shoulder swing to exercise the euler unwrap
+    trans = np.stack([1.0 * t, 0.1 * np.sin(t), 0.9 + 0.02 * np.sin(3 * t)], axis=1)
+    ns = types.SimpleNamespace(_offsets=torch.from_numpy(np.round(m.body_pos[None].astype(np.float32), decimals=5)),
+                               _parents=[-1, 0, 1, 2, 3, 0, 5, 6, 7, 0, 9, 10, 11, 12, 11, 14, 15, 16, 17, 11, 19, 20, 21, 22],
+                               smpl_2_mujoco=[SMPL_BONE_ORDER_NAMES.index(q) for q in SMPL_MUJOCO_NAMES], dt=1.0 / fps, filter_vel=True)
+    for name in ("forward_kinematics_batch",):
+        setattr(ns, name, types.MethodType(getattr(HB.Humanoid_Batch, name), ns))
+    ns._compute_velocity = HB.Humanoid_Batch._compute_velocity
+    ns._compute_angular_velocity = HB.Humanoid_Batch._compute_angular_velocity
+    out = HB.Humanoid_Batch.fk_batch(ns, torch.from_numpy(pose_aa[None]).float(), torch.from_numpy(trans[None]).float(), return_full=True, count_offset=True)
+    g = {k: out[k][0].numpy() for k in ("global_translation", "global_rotation", "global_velocity", "global_angular_velocity", "dof_pos", "dof_vels", "qpos", "qvel")}
+    g.update(pose_aa=pose_aa.reshape(F, 72).astype(np.float32), trans=trans.astype(np.float32), fps=fps)
+    np.savez_compressed(os.path.join(HERE, "motion_fk.npz"), **g)
+    print("motion_fk.npz:", {k: v.shape for k, v in g.items() if hasattr(v, "shape")}, "max|dof_pos|", np.abs(g["dof_pos"]).max())
+
+
+if __name__ == "__main__":
+    main()

@@ -180,3 +180,25 @@ def test_two_ppo_epochs_getup_plumbing():
         info = learner.update(sampler.sample(6))
         assert all(np.isfinite(v) for v in info.values()), info
     assert int(policy.norm.n) == 2 * 2 * 6 * 64 and not torch.equal(w0, policy.action_mean.weight)
+
+
+def test_amass_loader_tables_feed_motion_lib_and_cuda_fk():
+    """AMASS-style clip -> amass_tables -> MotionLibB200: the loader's numpy FK agrees with the CUDA kinematics kernel on the same
+    qpos (xpos 1e-5, xquat up to sign), and a MoCap reset from the gathered state reproduces it."""
+    from smplsim_b200.batched import HumanoidBatchB200
+    from smplsim_b200.motion_lib import MotionLibB200
+    from smplsim_b200.motion_loader import amass_tables
+    g = np.load(os.path.join(GOLDEN, "motion_fk.npz"))
+    env = HumanoidBatchB200(make_cfg(env="speed"), num_envs=16, seed=0)
+    tb = amass_tables(env.model, {"clip": {"pose_aa": g["pose_aa"], "trans": g["trans"], "fps": int(g["fps"])}}, fix_height="geom")
+    xp, xq = env.kinematics(torch.as_tensor(tb["qpos"], device="cuda:0"))
+    assert np.abs(xp.cpu().numpy().reshape(-1, 72) - tb["xpos"]).max() < 2e-5
+    a, b = xq.cpu().numpy().reshape(-1, 24, 4), tb["xquat"].reshape(-1, 24, 4)
+    assert np.minimum(np.abs(a - b).max(-1), np.abs(a + b).max(-1)).max() < 2e-5
+    lib = MotionLibB200(env, tb)
+    ids = torch.zeros(16, dtype=torch.int32, device="cuda:0")
+    tm = torch.linspace(0, float(tb["motion_lengths"][0]), 16, device="cuda:0")
+    st = lib.get_motion_state_intervaled(ids, tm)
+    env.reset(init_mode=2, qpos0=st["qpos"], qvel0=st["qvel"])
+    assert torch.allclose(env.qpos[:, :3], st["qpos"][:, :3], atol=1e-6) and torch.isfinite(env.obs_buf).all()
+    assert (env.qpos[:, 2] > 0.5).all()
