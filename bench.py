@@ -31,11 +31,25 @@ SIGMA = float(np.exp(-2.5))          # learning/simple_mlp.yaml:11-12 fixed log_
 B_ALG_BYTES = 2682                   # (223 read + 447.5 written) fp32 words per env-step
 B_ALG_STALE_BYTES = 1208             # + (qpos,qvel) of the last forward pass written + read (quirk-Q1 parity carry)
 WORKLOAD = "cfg2: 4096 SMPL envs/GPU, env=speed, uhc_pd (stable PD), obs_v1=292, 15 substeps @450Hz, autoreset"
+# --workload: the headline (cfg2, default) and the other single-GPU shapes of BASELINE.json's configs (variants, not the bench line)
+WORKLOADS = {
+    "cfg2": dict(env="speed", robot="smpl_humanoid", overrides={}, envs=4096, balg=2682, desc=WORKLOAD),
+    "cfg2-pd": dict(env="speed", robot="smpl_humanoid", overrides={"env.control_mode": "pd"}, envs=4096, balg=2682,
+                    desc="cfg2 variant: explicit PD (control_mode=pd), 4096 SMPL envs/GPU"),
+    "cfg2-v2": dict(env="speed", robot="smpl_humanoid", overrides={"env.self_obs_v": 2, "robot.create_vel_sensors": True}, envs=4096, balg=2958,
+                    desc="cfg2 variant: self_obs_v=2 (obs 361), 4096 SMPL envs/GPU"),
+    "cfg3": dict(env="reach", robot="smpl_humanoid", overrides={"env.self_obs_v": 2, "robot.create_vel_sensors": True}, envs=16384, balg=2974,
+                 desc="cfg3: 16384 SMPL envs/GPU, env=reach, self_obs_v=2 (obs 361), uhc_pd"),
+    "cfg5": dict(env="getup", robot="smplx_humanoid", overrides={}, envs=4096, balg=5698,
+                 desc="cfg5 shard: 4096 SMPL-X (52 bodies) envs/GPU, env=getup (Fall init), obs_v1, uhc_pd"),
+}
+_WL = "cfg2"
 
 
 def make_cfg():
     from smplsim_b200.cfg import make_cfg as mk
-    return mk(env="speed")
+    w = WORKLOADS[_WL]
+    return mk(env=w["env"], robot=w["robot"], overrides=w["overrides"])
 
 
 class ClockSampler:
@@ -166,7 +180,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    global _WL, WORKLOAD, B_ALG_BYTES
+    _WL = args.workload
+    WORKLOAD, B_ALG_BYTES = WORKLOADS[_WL]["desc"], WORKLOADS[_WL]["balg"]
+    if args.envs_per_gpu == ENVS_PER_GPU:
+        args.envs_per_gpu = WORKLOADS[_WL]["envs"]
     if args.impl == "reference":
         return run_reference(args)
 
@@ -269,7 +289,7 @@ def main():
         achieved = balg * N / (k_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "k_step_dram_bytes.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and _WL == "cfg2":
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
@@ -279,7 +299,7 @@ def main():
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": N, "global_envs": total_envs, "substeps_per_step": int(env.envcfg.nsubsteps),
-                       "control_mode": "uhc_pd", "spd_inertia": "stale" if env.envcfg.spd_stale else "fresh", "parallelism": f"env-shard x{world}",
+                       "control_mode": str(cfg.env.control_mode), "spd_inertia": "stale" if env.envcfg.spd_stale else "fresh", "parallelism": f"env-shard x{world}",
                        "kernel": f"v{env.kernel_version}", "smem_bytes_per_env": env.smem_bytes_per_env(),
                        "l2": "256 MiB flush buffer zeroed after every step inside the timed region (state ~11 MB < 126 MB L2)"},
             "substeps_per_s": value * int(env.envcfg.nsubsteps),
@@ -287,7 +307,7 @@ def main():
                     "steps": Ke, "note": "pinned host actions -> device, step, obs/reward/flags -> pinned host, stream sync every step"},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "k_step", "kernel_ms": k_ms, "alg_bytes_per_env_step": balg,
+                         "peak_source": peak_src, "kernel": f"k_step{env.kernel_version}" if env.kernel_version > 1 else "k_step", "kernel_ms": k_ms, "alg_bytes_per_env_step": balg,
                          "note": "15 fused substeps keep state on-chip: the kernel is FP32-issue/latency bound, not HBM bound (SURVEY.md 8d)"},
         }
         if not args.no_cpu_baseline and world == 1:
