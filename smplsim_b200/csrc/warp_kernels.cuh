@@ -846,6 +846,7 @@ __device__ __noinline__ int w_solve(const WModel<C>& M, float* sm, const WLane& 
       }
     }
     if (adopt) w_rows(M, sm, w, true, 0, 0.f, o4);
+    __syncwarp();   // w_rows loads acc2 / qstar (lane per slot) before the lane-per-element copies below overwrite them
     if (fin || adopt) {
       for (int d = w.li; d < M.nv; d += C::LPE) sm[C::qacc + d] = sm[C::qstar + d];
       if (adopt) for (int j = w.li; j < 6 * M.nb; j += C::LPE) sm[C::acc2 + j] = sm[C::acc + j];
