@@ -144,7 +144,7 @@ typedef struct SmplsimAux {
 typedef struct SmplsimHandle SmplsimHandle;
 
 const char* smplsim_last_error(void);
-int smplsim_version(void);
+int smplsim_version(void);   /* 110 = this header (100: before pid_* state and aux.status) */
 
 /* MjModel.from_xml_string + MjData + setup_humanoid_properties/setup_controller
  * (base_env.py:139-142, humanoid_env.py:262-323). */
