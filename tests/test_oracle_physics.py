@@ -140,3 +140,32 @@ def test_static_stance_force_balance_and_kkt():
     assert np.abs(f[r >= 0]).max() < 1e-9 if (r >= 0).any() else True
     # newton's third law in joint space: qfrc_constraint = J^T f
     assert np.abs(efc["J"].T @ f - np.array(e.qfrc_constraint)).max() < 1e-8 * max(1.0, np.abs(f).max())
+
+
+@pytest.mark.parametrize("name", ["smpl", "smplx"])
+def test_oracle_matches_mujoco_g4(name):
+    """G4: the restatement against real MuJoCo output (tests/golden/make_golden_mujoco.py).  Skipped until that fixture can be
+    generated -- there is no `mujoco` wheel in this image, hence DESIGN.md's "parity unpinned" for the physics."""
+    import os
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "mj_step_g4.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/mj_step_g4.npz absent (needs a real mujoco wheel): physics parity unpinned")
+    g = np.load(path)
+    cfg, om = make_models(robot=f"{name}_humanoid", control_mode="torque")
+    m = om.model
+    assert np.abs(np.asarray(m.body_mass) - g[f"{name}.body_mass"]).max() < 1e-6
+    n_checked = 0
+    for i in range(g[f"{name}.qpos"].shape[0]):
+        if g[f"{name}.ncon_self"][i]:
+            continue                                         # self-collision is not simulated (SURVEY 8 f4)
+        e = orc.OracleEnv(om)
+        e.qpos[:] = g[f"{name}.qpos"][i]; e.qvel[:] = g[f"{name}.qvel"][i]; e.qacc_warm[:] = g[f"{name}.qacc_warm"][i]
+        e.ctrl[:] = g[f"{name}.ctrl"][i]
+        e.mj_step()
+        ref_q, ref_v = g[f"{name}.qpos1"][i], g[f"{name}.qvel1"][i]
+        assert np.abs(e.qpos - ref_q).max() / max(1.0, np.abs(ref_q).max()) < 1e-6, i
+        assert np.abs(e.qvel - ref_v).max() / max(1.0, np.abs(ref_v).max()) < 1e-6, i
+        assert e.contact_mask == int(g[f"{name}.floor_geoms"][i]), i
+        n_checked += 1
+    assert n_checked > 0
