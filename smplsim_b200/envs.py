@@ -144,6 +144,20 @@ class HumanoidEnvB200(_EnvBase):
                                xpos=np.concatenate([z3, b.xpos[0].cpu().numpy()]), xquat=np.concatenate([z4, b.xquat[0].cpu().numpy()]),
                                sensordata=sens, contact=_Contacts(int(b.contact_mask[0].item())))
 
+    @property
+    def mj_model(self):
+        """The MjModel attributes the reference reads (humanoid_env.py:262-289,325-370; utils/mujoco_utils.py): sizes, names, joint
+        ranges, timestep.  Body / geom 0 is the world / floor, as in MuJoCo."""
+        m = self._b.model
+        rng = np.asarray(m.dof_range)
+        names = ["world"] + list(m.body_names)
+        joints = {n: SimpleNamespace(name=n, range=rng[6 + i].copy(), qposadr=np.array([7 + i]), dofadr=np.array([6 + i]))
+                  for i, n in enumerate(m.joint_names)}
+        return SimpleNamespace(nbody=m.nbody + 1, nq=m.nq, nv=m.nv, nu=m.nu, ngeom=len(m.geom_names) + 1, opt=SimpleNamespace(timestep=self.sim_timestep),
+                               body=lambda i: SimpleNamespace(name=names[i], id=i), joint=lambda n: joints[n],
+                               geom=lambda i: SimpleNamespace(name=(["floor"] + list(m.geom_names))[i], id=i),
+                               body_mass=np.concatenate([[0.0], np.asarray(m.body_mass)]))
+
     def get_qpos(self):
         return self._b.qpos[0].cpu().numpy().astype(np.float64)
 
@@ -155,6 +169,9 @@ class HumanoidEnvB200(_EnvBase):
 
     def get_body_xquat(self):
         return self._b.xquat[0].cpu().numpy().astype(np.float64)
+
+    def get_body_xpos_by_id(self, body_id):
+        return self.get_body_xpos()[body_id]
 
     def get_root_pos(self):
         return self.get_body_xpos()[0].copy()

@@ -37,6 +37,9 @@ def test_single_env_protocol_matches_oracle_getup():
     d = env.mj_data
     assert d.qpos.shape == (76,) and d.xpos.shape == (25, 3) and d.sensordata.shape == (144,)
     assert set(d.contact.geom1.tolist()) <= {0}
+    mm = env.mj_model                                  # the MjModel reads of humanoid_env.py:262-289
+    assert mm.nbody == 25 and mm.nv == 75 and mm.body(1).name == "Pelvis" and abs(mm.opt.timestep - 1 / 450) < 1e-12
+    assert np.allclose(mm.joint("L_Hip_x").range, [-np.pi, np.pi]) and abs(mm.body_mass.sum() - 71.81) < 0.01
 
 
 def test_gym_vect_env_autoreset_and_final_observation():
