@@ -195,16 +195,20 @@ def run_reference(args):
     cb = None
     budget = 150.0 / max(1, args.steps + args.warmup)      # the whole run ends within a few minutes
     secs = max(0.25, min(20.0, budget))
+    if os.environ.get("SMPLSIM_BENCH_SECS"):              # tests: shrink the bounded sample
+        secs = float(os.environ["SMPLSIM_BENCH_SECS"])
+    t_run = time.perf_counter()
     for i in range(args.warmup + args.steps):
         cb = co.sample(secs)
         if i >= args.warmup:
             per.append(cb["value"])
     val = float(np.mean(per))
+    ms_per = (time.perf_counter() - t_run) * 1e3 / max(1, args.warmup + args.steps)
     cb["value"] = val
     cb["sample"] = f"{args.steps} samples, each: " + cb["sample"]
     line = {
         "impl": "reference", "metric": "env-steps/sec SMPL humanoid (speed task, 15 substeps/step)", "value": val, "unit": "env-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU oracle port; each step = one bounded sample"},
         "cpu_baseline": cb, "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
     }
