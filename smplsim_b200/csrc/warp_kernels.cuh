@@ -629,11 +629,18 @@ __device__ __noinline__ unsigned long long w_collide(const WModel<C>& M, float* 
           float R1 = R0 / fmaxf(M.impratio, 1e-15f), mu = M.mu * sqrtf(R1 / R0);
           sm[C::cD + c2] = 1.0f / (2.f * mu * mu * R0);
           float kterm = M.K * imp * pm;
+          int guess = 0;      // rows with aref > 0 (active if the body ends up with ~zero acceleration along the row)
 #pragma unroll 1
-          for (int k = 0; k < 4; k++) sm[C::caref + 4 * c2 + k] = -M.B * dot6(w_wrench(M, cp, t1, k), v) - kterm;
-          // warmset: start from the working set this slot ended the previous substep with (new contacts: all rows active)
+          for (int k = 0; k < 4; k++) {
+            float ar = -M.B * dot6(w_wrench(M, cp, t1, k), v) - kterm;
+            sm[C::caref + 4 * c2 + k] = ar;
+            if (ar > 0.f) guess |= 2 << k;
+          }
+          // warmset: start from the working set this slot ended the previous substep with (new contacts: all rows active,
+          // or -- bit 3 -- the aref-sign guess)
           int pf = cflag[c2];
-          int inh = (M.warmset & 1) ? ((pf & 1) ? (pf & 30) : ((M.warmset & 2) ? 0 : 30)) : ((M.warmset & 4) ? 30 : 0);
+          int fresh = (M.warmset & 8) ? guess : ((M.warmset & 2) ? 0 : 30);
+          int inh = (M.warmset & 1) ? ((pf & 1) ? (pf & 30) : fresh) : ((M.warmset & 4) ? 30 : 0);
           cflag[c2] = M.warmset ? (1 | inh) : 1;
         }
         mask |= 1ull << (g + 1);
