@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Print CUDA-vs-oracle error tables (development aid; run under gpurun)."""
+"""Print CUDA-vs-oracle error tables (development aid next to the parity tests -- it uses the oracle, so it lives under tests/;
+run under gpurun: python tests/gpu_debug_tables.py)."""
 import os
 import sys
 import time
@@ -8,7 +9,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from oracle import oracle as orc  # noqa: E402
 from smplsim_b200.batched import HumanoidBatchB200  # noqa: E402
 from util_states import airborne_states, make_models, relerr, rollout_states  # noqa: E402
