@@ -89,6 +89,18 @@ class OracleModel:
         m = model_from_cfg(cfg)
         return cls(m, env_cfg_from(cfg, m, seed=seed))
 
+    def set_self_collision(self, enable: bool = True):
+        """ORACLE-ONLY groundwork for SURVEY 8 f4 (the CUDA product does not simulate self-collision): capsule / sphere geom pairs
+        with MuJoCo's filters (same body, parent-child, contype / conaffinity, <contact><exclude>).  Off by default."""
+        m = self.model
+        ex = np.array([[m.body_names.index(a), m.body_names.index(b)] for a, b in m.excludes], dtype=np.int32).reshape(-1, 2)
+        ct = np.ascontiguousarray(m.geom_contype, dtype=np.int32); ca = np.ascontiguousarray(m.geom_conaffinity, dtype=np.int32)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+        L = lib()
+        L.orc_set_self_collision.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
+        L.orc_set_self_collision(self.ptr, int(enable), ip(ct), ip(ca), ip(np.ascontiguousarray(ex)), int(ex.shape[0]))
+        return self
+
     def __del__(self):
         try:
             lib().orc_model_free(self.ptr)
@@ -165,7 +177,11 @@ class OracleEnv:
 
     def contacts(self):
         n = self.ncon
-        return dict(geom=self._con_geom[:n].copy() + 1, dist=self._con_dist[:n].copy(), pos=self._con_pos[:n].copy(),
+        L = lib()
+        L.orc_con_geom1.restype = C.POINTER(C.c_int)
+        L.orc_con_geom1.argtypes = [C.c_void_p]
+        g1 = np.ctypeslib.as_array(L.orc_con_geom1(self.ptr), shape=(256,))[:n].copy() + 1     # 0 = floor, else MuJoCo geom id
+        return dict(geom1=g1, geom=self._con_geom[:n].copy() + 1, dist=self._con_dist[:n].copy(), pos=self._con_pos[:n].copy(),
                     frame=self._con_frame[:n].copy())
 
     def efc(self):

@@ -135,6 +135,8 @@ class ModelDesc:
     act_offset: np.ndarray
     excludes: List[tuple]
     qpos0: np.ndarray
+    geom_contype: Optional[np.ndarray] = None      # [ng] collision filter bits (only the oracle's opt-in self-collision reads them)
+    geom_conaffinity: Optional[np.ndarray] = None
 
     # ------------------------------------------------------------------ sizes
     @property
@@ -400,7 +402,8 @@ def build_model(p: ParsedMJCF, *, timestep: float = 1.0 / 450.0, contact_bodies:
         margin=float(margins.pop()), friction=fr, solref=p.solref.copy(), solimp=p.solimp.copy(), impratio=1.0,
         timestep=float(timestep), gravity=np.array([0.0, 0.0, -9.81]),
         act_kp=kp, act_kd=kd, act_torque_lim=tl, act_scale=scale, act_offset=offset,
-        excludes=list(p.excludes), qpos0=qpos0)
+        excludes=list(p.excludes), qpos0=qpos0, geom_contype=np.array([g.contype for g in p.geoms], np.int32),
+        geom_conaffinity=np.array([g.conaffinity for g in p.geoms], np.int32))
     # body 0 of the tree hangs off the world: MuJoCo root body_quat is applied at qpos0 only
     m.body_quat[0] = np.array([1.0, 0, 0, 0])
     m.body_invweight0, m.dof_invweight0 = _invweight0(m)
