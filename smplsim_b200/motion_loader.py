@@ -26,6 +26,18 @@ import numpy as np
 SMPL_BONE_ORDER_NAMES = ["Pelvis", "L_Hip", "R_Hip", "Torso", "L_Knee", "R_Knee", "Spine", "L_Ankle", "R_Ankle", "Chest", "L_Toe", "R_Toe",
                          "Neck", "L_Thorax", "R_Thorax", "Head", "L_Shoulder", "R_Shoulder", "L_Elbow", "R_Elbow", "L_Wrist", "R_Wrist",
                          "L_Hand", "R_Hand"]       # the SMPL kinematic-tree order AMASS poses come in (smpl_joint_names.py:19-44)
+_FINGERS = [f + str(i) for f in ("Index", "Middle", "Pinky", "Ring", "Thumb") for i in (1, 2, 3)]
+SMPLH_BONE_ORDER_NAMES = SMPL_BONE_ORDER_NAMES[:22] + ["L_" + f for f in _FINGERS] + ["R_" + f for f in _FINGERS]   # smpl_joint_names.py:46-99 (52)
+
+
+def bone_order_for(model):
+    """Pose-file joint order of the humanoid class: 24-body SMPL, or the 52-body SMPL-H / SMPL-X body (Humanoid_Batch uses
+    SMPLH_BONE_ORDER_NAMES for both, torch_smpl_humanoid_batch.py:47-71)."""
+    names = list(model.body_names)
+    for order in (SMPL_BONE_ORDER_NAMES, SMPLH_BONE_ORDER_NAMES):
+        if sorted(names) == sorted(order):
+            return order
+    raise NotImplementedError("fk_motion: the model is neither the 24-body SMPL nor the 52-body SMPL-H/X humanoid")
 
 
 def aa_to_quat(aa: np.ndarray) -> np.ndarray:
@@ -102,11 +114,13 @@ def _qmul(a, b):
 
 
 def fk_motion(model, pose_aa: np.ndarray, trans: np.ndarray, fps: float, filter_vel: bool = True) -> Dict[str, np.ndarray]:
-    """One clip: ``pose_aa [F, 24, 3]`` (SMPL joint order), ``trans [F, 3]`` -> per-frame state in MuJoCo order (fk_batch, return_full)."""
+    """One clip: ``pose_aa [F, J, 3]`` (SMPL joint order, J = 24; SMPL-H order, J = 52), ``trans [F, 3]`` -> per-frame state in MuJoCo
+    body order (fk_batch, return_full)."""
     names = list(model.body_names)
-    if sorted(names) != sorted(SMPL_BONE_ORDER_NAMES):
-        raise NotImplementedError("fk_motion: AMASS SMPL clips need the 24-body SMPL humanoid (SMPL-H/X clips: not built)")
-    s2m = [SMPL_BONE_ORDER_NAMES.index(n) for n in names]
+    order = bone_order_for(model)
+    if pose_aa.shape[1] != len(order):
+        raise ValueError(f"pose_aa has {pose_aa.shape[1]} joints, the model needs {len(order)}")
+    s2m = [order.index(n) for n in names]
     F = pose_aa.shape[0]
     dt = 1.0 / float(fps)
     pose_quat = aa_to_quat(pose_aa.astype(np.float64))
@@ -133,7 +147,7 @@ def fk_motion(model, pose_aa: np.ndarray, trans: np.ndarray, fps: float, filter_
     angvel = axis * ang[..., None] / dt
     if filter_vel:
         vel, angvel = _gauss(vel), _gauss(angvel)
-    dof_pos = fix_continuous_dof(mat_to_euler_xyz(mats)[:, 1:])        # [F, 23, 3]
+    dof_pos = fix_continuous_dof(mat_to_euler_xyz(mats)[:, 1:])        # [F, J-1, 3]
     dof_vel = (dof_pos[1:] - dof_pos[:-1]) / dt
     dof_vel = np.concatenate([dof_vel, dof_vel[-1:]], 0)
     qpos = np.concatenate([root_pos, pose_quat[:, 0], dof_pos.reshape(F, -1)], -1)
@@ -189,11 +203,14 @@ def amass_tables(model, motions: Union[str, Dict[str, dict], Iterable[dict]], fi
         if max_length != -1 and F >= max_length:
             s = int(rng.integers(0, F - max_length + 1))
             pose, trans = pose[s:s + max_length], trans[s:s + max_length]
-        if pose.shape[1] == 156:                                       # SMPL-H body: keep the 22 body joints, zero the hands (:128-129)
+        nj = len(bone_order_for(model))
+        if pose.shape[1] == 156 and nj == 24:                          # SMPL-H clip on the SMPL body: keep the 22 body joints, zero the hands (:128-129)
             pose = np.concatenate([pose[:, :66], np.zeros((pose.shape[0], 6))], 1)
-        if pose.shape[1] != 72:
+        if pose.shape[1] == 72 and nj == 52:                           # SMPL clip on the SMPL-H/X body: body joints, open hands
+            pose = np.concatenate([pose[:, :66], np.zeros((pose.shape[0], 90))], 1)
+        if pose.shape[1] != 3 * nj:
             raise ValueError(f"pose_aa must be [F,72] or [F,156], got {pose.shape}")
-        pose = pose.reshape(-1, 24, 3)
+        pose = pose.reshape(-1, nj, 3)
         if randomize_heading:                                          # :138-144
             yaw = np.pi * (2 * rng.random() - 1.0)
             qh = np.array([np.cos(yaw / 2), 0.0, 0.0, np.sin(yaw / 2)])

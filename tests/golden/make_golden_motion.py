@@ -51,5 +51,33 @@ def main():
     print("motion_fk.npz:", {k: v.shape for k, v in g.items() if hasattr(v, "shape")}, "max|dof_pos|", np.abs(g["dof_pos"]).max())
 
 
+def main_smplh():
+    """Same through the SMPL-H / SMPL-X branch of Humanoid_Batch (52 joints, :47-71)."""
+    from smpl_sim.smpllib.smpl_joint_names import SMPLH_BONE_ORDER_NAMES, SMPLH_MUJOCO_NAMES
+    HB.EasyDict = _Dict
+    m = load_model("smplx")
+    assert list(m.body_names) == list(SMPLH_MUJOCO_NAMES)
+    rng = np.random.default_rng(9)
+    F, fps = 24, 30
+    t = np.arange(F) / fps
+    amp = rng.uniform(0.0, 0.4, (52, 3)); frq = rng.uniform(0.3, 1.5, (52, 3)); ph = rng.uniform(0, 6.28, (52, 3))
+    pose_aa = amp[None] * np.sin(2 * np.pi * frq[None] * t[:, None, None] + ph[None])
+    pose_aa[:, 0] = np.array([1.2, 1.2, 1.2])[None]
+    trans = np.stack([0.5 * t, 0 * t, 0.9 + 0 * t], axis=1)
+    parents = [-1, 0, 1, 2, 3, 0, 5, 6, 7, 0, 9, 10, 11, 12, 11, 14, 15, 16, 17, 18, 19, 17, 21, 22, 17, 24, 25, 17, 27, 28, 17, 30, 31, 11, 33, 34,
+               35, 36, 37, 38, 36, 40, 41, 36, 43, 44, 36, 46, 47, 36, 49, 50]
+    ns = types.SimpleNamespace(_offsets=torch.from_numpy(np.round(m.body_pos[None].astype(np.float32), decimals=5)), _parents=parents,
+                               smpl_2_mujoco=[SMPLH_BONE_ORDER_NAMES.index(q) for q in SMPLH_MUJOCO_NAMES], dt=1.0 / fps, filter_vel=True)
+    ns.forward_kinematics_batch = types.MethodType(HB.Humanoid_Batch.forward_kinematics_batch, ns)
+    ns._compute_velocity = HB.Humanoid_Batch._compute_velocity
+    ns._compute_angular_velocity = HB.Humanoid_Batch._compute_angular_velocity
+    out = HB.Humanoid_Batch.fk_batch(ns, torch.from_numpy(pose_aa[None]).float(), torch.from_numpy(trans[None]).float(), return_full=True, count_offset=True)
+    g = {k: out[k][0].numpy() for k in ("global_translation", "global_rotation", "dof_pos", "qpos", "qvel")}
+    g.update(pose_aa=pose_aa.reshape(F, 156).astype(np.float32), trans=trans.astype(np.float32), fps=fps)
+    np.savez_compressed(os.path.join(HERE, "motion_fk_smplh.npz"), **g)
+    print("motion_fk_smplh.npz:", {k: v.shape for k, v in g.items() if hasattr(v, "shape")})
+
+
 if __name__ == "__main__":
     main()
+    main_smplh()
