@@ -50,9 +50,10 @@ _SYMBOLS = {
     "smplsim_warps_per_block": (C.c_int, [C.c_void_p]),
     "smplsim_kernel_version": (C.c_int, [C.c_void_p]),
     "smplsim_schedule_steps": (C.c_int, [C.c_void_p]),
+    "smplsim_records_in_tmem": (C.c_int, [C.c_void_p]),
 }
 # the entry points include/smplsim.h declares (checked by tests/test_abi.py)
-_INTROSPECTION = ("smplsim_smem_bytes_per_env", "smplsim_warps_per_block", "smplsim_kernel_version", "smplsim_schedule_steps")
+_INTROSPECTION = ("smplsim_smem_bytes_per_env", "smplsim_warps_per_block", "smplsim_kernel_version", "smplsim_schedule_steps", "smplsim_records_in_tmem")
 HEADER_SYMBOLS = [s for s in _SYMBOLS if s not in _INTROSPECTION]
 
 

@@ -31,8 +31,7 @@ class HumanoidBatchB200:
 
     def __init__(self, cfg: Any, num_envs: Optional[int] = None, device: str = "cuda:0", seed: Optional[int] = None,
                  model: Optional[ModelDesc] = None, rank: int = 0, with_aux: bool = True):
-        if not torch.cuda.is_available():
-            raise RuntimeError("HumanoidBatchB200 needs a CUDA device (there is no CPU fallback for the stepper)")
+        self._require_device(device)
         self.cfg = cfg
         e = cfg.env
         self.num_envs = int(num_envs if num_envs is not None else (e.get("num_envs", 1) if hasattr(e, "get") else 1))
@@ -43,9 +42,9 @@ class HumanoidBatchB200:
         self.envcfg = env_cfg_from(cfg, self.model, seed=self.seed)
         self._cmodel = self.model.c_struct()
         self._h = C.c_void_p()
-        L = _lib.lib()
-        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        _lib.check(L.smplsim_create(C.addressof(self._cmodel), C.addressof(self.envcfg), self.num_envs, dev_index, C.byref(self._h)))
+        L = self._L()
+        dev_index = self._device_index()
+        self._check(L.smplsim_create(C.addressof(self._cmodel), C.addressof(self.envcfg), self.num_envs, dev_index, C.byref(self._h)))
         self.num_obs = L.smplsim_obs_dim(self._h)
         self.num_actions = self.model.nu
         self.dt = float(self.model.timestep * self.envcfg.nsubsteps)
@@ -94,10 +93,25 @@ class HumanoidBatchB200:
     def __del__(self):
         try:
             if self._h:
-                _lib.lib().smplsim_destroy(self._h)
+                self._L().smplsim_destroy(self._h)
                 self._h = C.c_void_p()
         except Exception:
             pass
+
+    # ------------------------------------------------------------------ binding to libsmplsim_b200.so (CUDA only)
+    def _require_device(self, device):
+        if not torch.cuda.is_available():
+            raise RuntimeError("HumanoidBatchB200 needs a CUDA device (there is no CPU fallback for the stepper)")
+
+    def _L(self):
+        return _lib.lib()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.SmplsimError(f"libsmplsim_b200 error {rc}: {self._L().smplsim_last_error().decode()}")
+
+    def _device_index(self):
+        return self.device.index if self.device.index is not None else torch.cuda.current_device()
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -118,7 +132,7 @@ class HumanoidBatchB200:
         if qpos0 is not None:
             qpos0 = qpos0.to(self.device, torch.float32).contiguous()
             qvel0 = qvel0.to(self.device, torch.float32).contiguous()
-        _lib.check(_lib.lib().smplsim_reset(self._h, C.byref(self._state), _ptr(mask), int(init_mode), _ptr(qpos0), _ptr(qvel0),
+        self._check(self._L().smplsim_reset(self._h, C.byref(self._state), _ptr(mask), int(init_mode), _ptr(qpos0), _ptr(qvel0),
                                             _ptr(self.obs_buf), C.byref(self._aux), self._stream()))
         self.gpu_launches += 1
         self._keep = (mask, qpos0, qvel0)
@@ -135,7 +149,7 @@ class HumanoidBatchB200:
             a = torch.clamp(a, -1.0, 1.0)      # action_space Box(-1,1) (humanoid_env.py:180-184; agent.py:153-161)
         a = a.contiguous()
         assert a.shape == (self.num_envs, self.num_actions)
-        _lib.check(_lib.lib().smplsim_step(self._h, C.byref(self._state), _ptr(a), _ptr(self.obs_buf), _ptr(self.rew_buf),
+        self._check(self._L().smplsim_step(self._h, C.byref(self._state), _ptr(a), _ptr(self.obs_buf), _ptr(self.rew_buf),
                                            _ptr(self.terminate_buf), _ptr(self.truncate_buf), C.byref(self._aux), self._stream()))
         self.gpu_launches += 1
         torch.bitwise_or(self.terminate_buf, self.truncate_buf, out=self.reset_buf)
@@ -146,7 +160,7 @@ class HumanoidBatchB200:
     def mj_step(self, ctrl: torch.Tensor, nsub: int = 1):
         """data.ctrl[:] = ctrl; mujoco.mj_step x nsub."""
         c = ctrl.to(self.device, torch.float32).contiguous()
-        _lib.check(_lib.lib().smplsim_mj_step(self._h, C.byref(self._state), _ptr(c), int(nsub), C.byref(self._aux), self._stream()))
+        self._check(self._L().smplsim_mj_step(self._h, C.byref(self._state), _ptr(c), int(nsub), C.byref(self._aux), self._stream()))
         self.gpu_launches += 1
         self._keep_a = c
 
@@ -155,7 +169,7 @@ class HumanoidBatchB200:
         n = q.shape[0]
         xpos = torch.empty(n, self.model.nbody, 3, dtype=torch.float32, device=self.device)
         xquat = torch.empty(n, self.model.nbody, 4, dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().smplsim_kinematics(self._h, _ptr(q), _ptr(xpos), _ptr(xquat), n, self._stream()))
+        self._check(self._L().smplsim_kinematics(self._h, _ptr(q), _ptr(xpos), _ptr(xquat), n, self._stream()))
         self.gpu_launches += 1
         return xpos, xquat
 
@@ -166,7 +180,7 @@ class HumanoidBatchB200:
         n, nb = xpos.shape[0], self.model.nbody
         dim = (1 if self.envcfg.root_height_obs else 0) + 3 * (nb - 1) + 6 * nb + (6 + self.model.nu if version == 1 else 6 * nb)
         obs = torch.empty(n, dim, dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().smplsim_self_obs(self._h, version, _ptr(qvel), _ptr(xpos), _ptr(xquat), _ptr(linvel), _ptr(angvel),
+        self._check(self._L().smplsim_self_obs(self._h, version, _ptr(qvel), _ptr(xpos), _ptr(xquat), _ptr(linvel), _ptr(angvel),
                                                _ptr(obs), n, self._stream()))
         self.gpu_launches += 1
         return obs
@@ -179,16 +193,16 @@ class HumanoidBatchB200:
         self.qvel_fwd.copy_(self.qvel)
 
     def smem_bytes_per_env(self):
-        return _lib.lib().smplsim_smem_bytes_per_env(self._h)
+        return self._L().smplsim_smem_bytes_per_env(self._h)
 
     @property
     def kernel_version(self) -> int:
-        """3: default warp kernels (warp_kernels.cuh); 1: generic warp-per-env fallback; 2 / 4: experimental (SMPLSIM_KERNEL)."""
-        return _lib.lib().smplsim_kernel_version(self._h)
+        """5: lane-chain kernels (csrc/lane_kernels.cuh)."""
+        return self._L().smplsim_kernel_version(self._h)
 
     @property
     def schedule_steps(self) -> int:
-        return _lib.lib().smplsim_schedule_steps(self._h)
+        return self._L().smplsim_schedule_steps(self._h)
 
 
 class GymVectEnvB200:

@@ -1,65 +1,10 @@
-// dev_model.cuh -- device-resident constant table + per-env shared-memory layout.
-//
-// The table is the float32 image of SmplsimModelDesc (include/smplsim.h) plus host-derived
-// schedule data (tree levels, child lists, contact slots).  One copy per handle in global
-// memory; it is tiny (a few KB) and stays resident in L1/L2, read through the read-only path.
+// dev_model.cuh -- small device math shared by the kernels: 3-vectors, wxyz quaternions, spatial 6-vectors, symmetric 6x6
+// (upper triangle), rigid-body inertia about a reference point, Philox4x32-10.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/smplsim.h"
-
-#define SM_MAXB 64    // bodies
-#define SM_MAXV 192   // dofs
-#define SM_MAXG 64    // geoms
-#define SM_MAXL 16    // tree levels
-#define SM_MAXSLOT 128 // contact slots (sum over geoms of max contacts)
-#define SM_WARPS_PER_BLOCK 4
-#define SM_MAXSCHED 20
-
-struct DevModel {
-  int nb, nq, nv, nu, ng, nlevel, nslot;
-  // tree
-  int parent[SM_MAXB], dofadr[SM_MAXB], dofnum[SM_MAXB], depth[SM_MAXB];
-  int level_adr[SM_MAXL + 1], level_list[SM_MAXB];   // bodies grouped by depth
-  int child_adr[SM_MAXB + 1], child_list[SM_MAXB];
-  int dof_body[SM_MAXV];
-  float bpos[SM_MAXB][3], bquat[SM_MAXB][4], mass[SM_MAXB], ipos[SM_MAXB][3], inertia[SM_MAXB][6], tran_iw0[SM_MAXB];
-  float axis[SM_MAXV][3], arm[SM_MAXV], diw0[SM_MAXV], range[SM_MAXV][2];
-  int limited[SM_MAXV];
-  // geoms and their contact slots
-  int gtype[SM_MAXG], gbody[SM_MAXG], slot_adr[SM_MAXG + 1];
-  int bgeom_adr[SM_MAXB + 1], bgeom_list[SM_MAXG];    // geoms per body
-  int slot_geom[SM_MAXSLOT];
-  float gpos[SM_MAXG][3], gmat[SM_MAXG][9], gsize[SM_MAXG][3];
-  unsigned long long legal_mask;                       // bit g+1: floor contact with geom g is legal; bit 0 set
-  float plane_pos[3], plane_n[3], t1_default[3];
-  float margin, mu, impratio, solimp[5], imp_a, imp_b, K, B, h, grav[3];
-  // actuators
-  float kp[SM_MAXV], kd[SM_MAXV], tlim[SM_MAXV], ascale[SM_MAXV], aoffset[SM_MAXV];
-  SmplsimEnvCfg cfg;
-  int obs_dim, self_obs_dim;
-  int rowpar;                           // 1: row-parallel sweeps (8 lanes per body) when LPE == 32
-  int warmset;                          // 1: solver starts from the previous substep's working set per contact slot
-  float ls_tol;                         // line-search stop: |derivative| <= ls_tol * |derivative at 0|
-  int dirtypath;                        // 1: solver iterations >= 2 re-sweep only the bodies on paths from constraint rows to the root
-  int sched_T, sched[SM_MAXSCHED][4];   // 4-slot list schedule of the inward sweep (row-parallel kernels); sched_T = 0: none
-  int sched_nd[SM_MAXSCHED], sched_nc[SM_MAXSCHED], sched_ns[SM_MAXSCHED];  // per step: max dofs / children / contact slots (uniform loop bounds)
-};
-
-// Per-env scratch in shared memory: offsets (in 4-byte words) computed on the host.
-struct EnvLayout {
-  int qpos, qvel, act, tau, qacc, qwarm;
-  int xpos, xquat, xmat, ax, vel, abias, pb, irb, IA, pA, U, Dinv, u, acc;
-  int spd_ax, spd_xpos, spd_U, spd_Dinv, spd_ab;
-  int tin, dadd, qstar;       // generalized force fed to the force pass, joint-diagonal additions, trial qacc [nv]
-  int tsk;                    // task scalars: target[4], change_step, cur_t, recovery, rng (8 words)
-  int lD, laref, lr, lphi, lrs, lflag;   // joint-limit rows, one per dof
-  int cpos, ct1, cD, caref, cr, cphi, crs, cflag;  // contact slots
-  int sens;                   // body linvel/angvel of the last forward pass [nb*6]
-  int obs;                    // staging for the observation row
-  int total;                  // words per env
-};
 
 // ----------------------------------------------------------------------------- small math
 struct V3 { float x, y, z; };

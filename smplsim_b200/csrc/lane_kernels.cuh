@@ -1,0 +1,1527 @@
+// lane_kernels.cuh -- the stepper (v5): lane-chain Articulated-Body sweeps, 8 lanes per env, 4 envs per warp.
+//
+// Replaces, for N envs in lockstep, the body of HumanoidEnv.step (smpl_sim/envs/base_env.py:86-100):
+//   physics_step      15 x [ctrler.control + mujoco.mj_step]          smpl_sim/envs/humanoid_env.py:439-453, controllers.py:116-190
+//   post_physics_step mj_kinematics, self obs v1/v2, task obs, reward  smpl_sim/envs/humanoid_env.py:388-403,455-469,565-688
+//   reset             Default / Fall / MoCap                           smpl_sim/envs/humanoid_env.py:471-512
+//
+// Mapping (driven by the round-1 profile, profiles/r1_k_step3_final.md: 4.8 of 32 lanes active, 15.9 KB of shared memory
+// per env -> two waves at 4 096 envs):
+//   * an env is stepped by LM_LPE = 8 lanes; a lane walks a kinematic chain, one body per sweep step (host list schedule in
+//     LHdr::sched).  Along a chain the sweep state (articulated inertia 21 + bias force 6 inward; pose / velocity /
+//     acceleration outward) is handed from step to step IN REGISTERS; only tree junctions use shared-memory mailboxes;
+//   * per-body results a lane produces in one sweep and consumes itself in a later one (joint factors K = U/D, c = u/D, bias
+//     force) are lane-private "records": they live in Blackwell tensor memory (tcgen05.st / tcgen05.ld, 256 columns per
+//     lane, indexed by the warp-uniform sweep step) -- or in shared memory when the kernel is built with RECT = 0;
+//   * four fused sweeps per substep instead of seven passes:
+//       S1 outward: stable-PD acceleration (factors of the previous substep) -> torque, kinematics, velocities, bias forces,
+//                   rigid inertias, floor contacts and joint-limit rows
+//       S2 inward : articulated inertias + bias forces with the working set folded in -> K, c
+//       S3 outward: accelerations, residuals of the constraint rows (working-set test)
+//       [S2'/S3' : active-set Newton iterations, S2' only over the chains that carry rows; row-space exact line search]
+//       S4 inward : semi-implicit Euler of the body's own dofs, then the stable-PD factors (M + h Kd) for the next substep
+//   * everything else per env (~7.9 KB) stays in shared memory so that 28 envs (7 warps) live on one SM: 4 096 envs = one wave.
+// The mathematics (ABA in world-aligned spatial coordinates about the root origin, MuJoCo's soft-constraint rows as an
+// active-set problem solved by ABA passes) is that of round 1's warp_kernels.cuh; DESIGN.md section 2.
+#pragma once
+#include "dev_model.cuh"
+#include "lane_model.hpp"
+
+#define L_FULL 0xffffffffu
+#define L_SOLVER_MAXITER 16
+#define L_LS_MAXITER 24
+#define L_LS_NOISE 1e-4f     // line search: directional derivative below this fraction of its two cancelling parts = converged
+#define L_LS_MAXSTEP 16.f    // line search: never extrapolate further than this multiple of the Newton step
+#define L_MAXVAL 1e10f       // mjMAXVAL (mj_checkPos / Vel / Acc)
+// aux.status bits beyond mj_warning's 1 BADQPOS | 2 BADQVEL | 4 BADQACC
+#define L_ST_ROWS_DROPPED 8  // more simultaneous joint-limit rows than the kernel holds: the excess rows were not simulated
+#define L_ST_MAXITER 16      // the active-set solve stopped at L_SOLVER_MAXITER without reaching its fixed point
+
+// ------------------------------------------------------------------ compile-time sizes / per-env shared-memory layout (words)
+template <int NB_, int NV_, int NG_, int NS_, int NMBI_, int NMBO_, int NCS_, int NLS_, int RECT_>
+struct LCfg {
+  static constexpr int NB = NB_, NV = NV_, NQ = NV_ + 1, NU = NV_ - 6, NG = NG_, NS = NS_, NMBI = NMBI_, NMBO = NMBO_, NCS = NCS_, NLS = NLS_;
+  static constexpr int RECT = RECT_, LPE = LM_LPE, EPW = 32 / LM_LPE;
+  static constexpr int BODYW = 24, MBIW = 28, MBOW = 28, CONW = 24, LIMW = 8, RECW = 28, ROOTW = 44;
+  static constexpr int r4(int n) { return (n + 3) & ~3; }
+  static constexpr int qpos = 0, qvel = qpos + r4(NQ), qacc = qvel + r4(NV), act = qacc + r4(NV), tau = act + r4(NU), qstar = tau + r4(NU),
+                       body = qstar + r4(NV), mbi = body + BODYW * NB, mbo = mbi + MBIW * NMBI, root = mbo + MBOW * NMBO, con = root + ROOTW,
+                       lim = con + CONW * NCS, pfl = lim + LIMW * NLS, misc = pfl + r4((NS + 3) / 4), tsk = misc + 8,
+                       rec = tsk + 12, total_ = rec + (RECT ? 0 : RECW * NB);
+  static constexpr int total = total_ | 4;   // env stride: a multiple of 4 words (float4 rows) but not of 8 (bank spread)
+  // staging of the final kinematics / observation row: aliases the mailboxes, root factors and contact list (dead by then)
+  static constexpr int obs = mbi, xq = mbi + 4 * ((NB * 18 + 16 + 3) / 4);
+  static_assert(xq + 4 * NB <= lim, "observation / xquat staging does not fit the aliased region");
+};
+// misc words
+#define LMI_NCON 0
+#define LMI_NLIM 1
+// task words (as in round 1)
+#define L_TSK_CHANGE 4
+#define L_TSK_CURT 5
+#define L_TSK_RECOV 6
+#define L_TSK_RNG 7
+// body row: [ax 9 | xpos 3 | r10 10 | cinfo 1 | spare 1]
+#define LBR_AX 0
+#define LBR_X 9
+#define LBR_R10 12
+#define LBR_CI 22
+// contact entry: [info | cpos 3 | t1 3 | D | aref 4 | phi 4 | r 4 | rs 4]; info: bit0 present, bits1-4 working set, bits 8-15 geom, 16-23 slot
+#define LCE_INFO 0
+#define LCE_CP 1
+#define LCE_T1 4
+#define LCE_D 7
+#define LCE_AREF 8
+#define LCE_PHI 12
+#define LCE_R 16
+#define LCE_RS 20
+// limit entry: [dof | sg | D | aref | phi | flag | r | rs]
+#define LLE_DOF 0
+#define LLE_SG 1
+#define LLE_D 2
+#define LLE_AREF 3
+#define LLE_PHI 4
+#define LLE_FLAG 5
+#define LLE_R 6
+#define LLE_RS 7
+
+struct LLane {
+  int li;          // lane within the env group
+  int lane;        // lane within the warp
+  int gbase;       // first lane of the group
+  unsigned gmask;  // warp mask of this env's lanes
+  bool live;
+  int env;
+  unsigned tm;     // tensor-memory address of this warp's record block (RECT = 1)
+  float* gscr;     // overflow contact entries of this env (global scratch)
+  float* gsens;    // framelinvel / frameangvel of the last forward pass [6 nb] of this env (global scratch; NULL: not wanted)
+};
+
+template <class C> __device__ __forceinline__ const LHdr& l_hdr(const float* ms) { return *(const LHdr*)ms; }
+__device__ __forceinline__ const LBody* l_bodies(const float* ms) { return (const LBody*)((const char*)ms + ((const LHdr*)ms)->body_off); }
+__device__ __forceinline__ const LGeom* l_geoms(const float* ms) { return (const LGeom*)((const char*)ms + ((const LHdr*)ms)->geom_off); }
+
+__device__ __forceinline__ float l_gsum(float v) {
+#pragma unroll
+  for (int o = LM_LPE / 2; o > 0; o >>= 1) v += __shfl_xor_sync(L_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ bool l_gall(bool p, const LLane& w) { return (__ballot_sync(L_FULL, p) & w.gmask) == w.gmask; }
+__device__ __forceinline__ bool l_gany(bool p, const LLane& w) { return (__ballot_sync(L_FULL, p) & w.gmask) != 0u; }
+
+__device__ __forceinline__ void l_sincos(float x, float* s, float* c) {
+  float k = rintf(x * 0.63661977236758134f);
+  float r = fmaf(k, -1.5703125f, x);
+  r = fmaf(k, -4.837512969970703125e-4f, r);
+  r = fmaf(k, -7.549789954891882e-8f, r);
+  float z = r * r;
+  float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), z * r, r);
+  float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z * z, fmaf(-0.5f, z, 1.0f));
+  int q = ((int)k) & 3;
+  float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+  *s = (q & 2) ? -ss : ss;
+  *c = ((q + 1) & 2) ? -cc : cc;
+}
+
+__device__ __noinline__ float l_impedance(const LHdr& H, float pm) {
+  float x = fabsf(pm) / fmaxf(H.solimp[2], 1e-15f);
+  if (x >= 1.f) return H.solimp[1];
+  if (x <= 0.f) return H.solimp[0];
+  float y, pw = H.solimp[4];
+  if (pw == 2.0f) y = (x <= H.solimp[3]) ? H.imp_a * x * x : 1.f - H.imp_b * (1.f - x) * (1.f - x);
+  else if (pw < 1.0000001f && pw > 0.9999999f) y = x;
+  else y = (x <= H.solimp[3]) ? H.imp_a * __powf(x, pw) : 1.f - H.imp_b * __powf(1.f - x, pw);
+  return H.solimp[0] + y * (H.solimp[1] - H.solimp[0]);
+}
+
+// unit wrench of pyramid row k of a floor contact at cp (relative to the root origin): direction n +- mu t1 | n +- mu t2
+__device__ __forceinline__ S6 l_wrench(const LHdr& H, V3 cp, V3 t1, int k) {
+  V3 n = ld3(H.plane_n);
+  V3 t = (k < 2) ? t1 : cross(n, t1);
+  float sg = (k & 1) ? -H.mu : H.mu;
+  V3 dir = n + sg * t;
+  return s6(cross(cp, dir), dir);
+}
+
+// ------------------------------------------------------------------ lane records: [K 18 | c 3 | - | pb 6] per (lane, step)
+#ifndef SMPLSIM_EMU
+#define L_TM_LD4(a, r) asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]) : "r"(a))
+#define L_TM_LD8(a, r) asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]), "=r"((r)[4]), "=r"((r)[5]), "=r"((r)[6]), "=r"((r)[7]) : "r"(a))
+#define L_TM_LD16(a, r) asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+  : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]), "=r"((r)[4]), "=r"((r)[5]), "=r"((r)[6]), "=r"((r)[7]), "=r"((r)[8]), "=r"((r)[9]), "=r"((r)[10]), "=r"((r)[11]), "=r"((r)[12]), "=r"((r)[13]), "=r"((r)[14]), "=r"((r)[15]) : "r"(a))
+#define L_TM_ST4(a, r) asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"((r)[0]), "r"((r)[1]), "r"((r)[2]), "r"((r)[3]) : "memory")
+#define L_TM_ST8(a, r) asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(a), "r"((r)[0]), "r"((r)[1]), "r"((r)[2]), "r"((r)[3]), "r"((r)[4]), "r"((r)[5]), "r"((r)[6]), "r"((r)[7]) : "memory")
+#define L_TM_ST16(a, r) asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" \
+  ::"r"(a), "r"((r)[0]), "r"((r)[1]), "r"((r)[2]), "r"((r)[3]), "r"((r)[4]), "r"((r)[5]), "r"((r)[6]), "r"((r)[7]), "r"((r)[8]), "r"((r)[9]), "r"((r)[10]), "r"((r)[11]), "r"((r)[12]), "r"((r)[13]), "r"((r)[14]), "r"((r)[15]) : "memory")
+#define L_TM_WAIT_LD() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+#define L_TM_WAIT_ST() asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory")
+#else
+static inline uint32_t* emu_tm(unsigned a) {
+  int tid = emu::cur().tid, q = (tid >> 5) & 3;
+  if ((int)(a >> 16) != 32 * q) { fprintf(stderr, "emu: tensor-memory lane field %u of warp %d (quarter %d)\n", a >> 16, tid >> 5, q); abort(); }
+  int col = a & 0xffff;
+  if (col < 0 || col > 512) { fprintf(stderr, "emu: tensor-memory column %d\n", col); abort(); }
+  return emu::g_cta->tmem + (size_t)(32 * q + (tid & 31)) * 512 + col;
+}
+#define L_TM_LDN(a, r, n) do { uint32_t* p_ = emu_tm(a); if (((a) & 0xffff) + (n) > 512) { fprintf(stderr, "emu: tensor-memory overrun\n"); abort(); } for (int i_ = 0; i_ < (n); i_++) (r)[i_] = p_[i_]; } while (0)
+#define L_TM_STN(a, r, n) do { uint32_t* p_ = emu_tm(a); if (((a) & 0xffff) + (n) > 512) { fprintf(stderr, "emu: tensor-memory overrun\n"); abort(); } for (int i_ = 0; i_ < (n); i_++) p_[i_] = (r)[i_]; } while (0)
+#define L_TM_LD4(a, r) L_TM_LDN(a, r, 4)
+#define L_TM_LD8(a, r) L_TM_LDN(a, r, 8)
+#define L_TM_LD16(a, r) L_TM_LDN(a, r, 16)
+#define L_TM_ST4(a, r) L_TM_STN(a, r, 4)
+#define L_TM_ST8(a, r) L_TM_STN(a, r, 8)
+#define L_TM_ST16(a, r) L_TM_STN(a, r, 16)
+#define L_TM_WAIT_LD() do { } while (0)
+#define L_TM_WAIT_ST() do { } while (0)
+static inline unsigned __float_as_uint(float f) { return emu_bits(f); }
+static inline float __uint_as_float(unsigned u) { return emu_float(u); }
+#endif
+
+// K (3 x 6) and c (3) of the body this lane runs at step t.  Tensor-memory accesses are warp collectives: every lane of the
+// warp must reach them (callers keep them outside lane-divergent code); `keep` lanes write back what is there.
+template <class C>
+__device__ __forceinline__ void l_rec_ld_Kc(const LLane& w, float* sm, int t, int b, float* K, float* c) {
+  if (C::RECT) {
+    unsigned r[24], a = w.tm + (unsigned)(C::RECW * t);
+    L_TM_LD16(a, r);
+    L_TM_LD8(a + 16u, r + 16);
+    L_TM_WAIT_LD();
+#pragma unroll
+    for (int i = 0; i < 18; i++) K[i] = __uint_as_float(r[i]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) c[i] = __uint_as_float(r[18 + i]);
+  } else {
+    const float4* p = (const float4*)(sm + C::rec + C::RECW * (b < 0 ? 0 : b));
+    float4 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4], v5 = p[5];
+    K[0] = v0.x; K[1] = v0.y; K[2] = v0.z; K[3] = v0.w; K[4] = v1.x; K[5] = v1.y; K[6] = v1.z; K[7] = v1.w;
+    K[8] = v2.x; K[9] = v2.y; K[10] = v2.z; K[11] = v2.w; K[12] = v3.x; K[13] = v3.y; K[14] = v3.z; K[15] = v3.w;
+    K[16] = v4.x; K[17] = v4.y; c[0] = v4.z; c[1] = v4.w; c[2] = v5.x;
+  }
+}
+template <class C>
+__device__ __forceinline__ void l_rec_st_Kc(const LLane& w, float* sm, int t, int b, const float* K, const float* c, bool wr, bool preload) {
+  if (C::RECT) {
+    unsigned r[24], a = w.tm + (unsigned)(C::RECW * t);
+    if (preload) {   // some lanes keep their record (clean chains of a re-sweep): read - select - write
+      L_TM_LD16(a, r);
+      L_TM_LD8(a + 16u, r + 16);
+      L_TM_WAIT_LD();
+    } else {         // pb (cols 22, 23 of the x8 piece) is always preserved
+      L_TM_LD4(a + 20u, r + 20);
+      L_TM_WAIT_LD();
+    }
+    if (wr) {
+#pragma unroll
+      for (int i = 0; i < 18; i++) r[i] = __float_as_uint(K[i]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) r[18 + i] = __float_as_uint(c[i]);
+    }
+    L_TM_ST16(a, r);
+    L_TM_ST8(a + 16u, r + 16);
+    L_TM_WAIT_ST();
+  } else if (wr && b >= 0) {
+    float4* p = (float4*)(sm + C::rec + C::RECW * b);
+    p[0] = make_float4(K[0], K[1], K[2], K[3]); p[1] = make_float4(K[4], K[5], K[6], K[7]);
+    p[2] = make_float4(K[8], K[9], K[10], K[11]); p[3] = make_float4(K[12], K[13], K[14], K[15]);
+    p[4] = make_float4(K[16], K[17], c[0], c[1]);
+    ((float*)p)[20] = c[2];
+  }
+}
+template <class C>
+__device__ __forceinline__ S6 l_rec_ld_pb(const LLane& w, float* sm, int t, int b) {
+  float q[8];
+  if (C::RECT) {
+    unsigned r[8], a = w.tm + (unsigned)(C::RECW * t + 20);
+    L_TM_LD8(a, r);
+    L_TM_WAIT_LD();
+#pragma unroll
+    for (int i = 0; i < 8; i++) q[i] = __uint_as_float(r[i]);
+  } else {
+    const float* p = sm + C::rec + C::RECW * (b < 0 ? 0 : b) + 20;
+#pragma unroll
+    for (int i = 0; i < 8; i++) q[i] = p[i];
+  }
+  return s6(v3(q[2], q[3], q[4]), v3(q[5], q[6], q[7]));
+}
+template <class C>
+__device__ __forceinline__ void l_rec_st_pb(const LLane& w, float* sm, int t, int b, S6 pb, bool wr) {
+  if (C::RECT) {
+    unsigned r[8], a = w.tm + (unsigned)(C::RECW * t + 20);
+    L_TM_LD8(a, r);   // cols 20, 21 (c[2], spare) and a non-writing lane's pb are preserved
+    L_TM_WAIT_LD();
+    if (wr) {
+      r[2] = __float_as_uint(pb.a.x); r[3] = __float_as_uint(pb.a.y); r[4] = __float_as_uint(pb.a.z);
+      r[5] = __float_as_uint(pb.l.x); r[6] = __float_as_uint(pb.l.y); r[7] = __float_as_uint(pb.l.z);
+    }
+    L_TM_ST8(a, r);
+    L_TM_WAIT_ST();
+  } else if (wr && b >= 0) {
+    float* p = sm + C::rec + C::RECW * b + 22;
+    st3(p, pb.a); st3(p + 3, pb.l);
+  }
+}
+
+// contact entry c: the first NCS live in shared memory, the rest in this env's global scratch
+template <class C>
+__device__ __forceinline__ float* l_centry(float* sm, const LLane& w, int c) {
+  return c < C::NCS ? sm + C::con + C::CONW * c : w.gscr + (size_t)C::CONW * (c - C::NCS);
+}
+
+// S of hinge k of body row br (axis in world coordinates, moment about the root origin)
+__device__ __forceinline__ S6 l_hingeS(const float* br, int k) {
+  V3 a = ld3(br + LBR_AX + 3 * k);
+  return s6(a, cross(ld3(br + LBR_X), a));
+}
+__device__ __forceinline__ void l_s6arr(S6 s, float* o) { o[0] = s.a.x; o[1] = s.a.y; o[2] = s.a.z; o[3] = s.l.x; o[4] = s.l.y; o[5] = s.l.z; }
+__device__ __forceinline__ S6 l_arr6(const float* o) { return s6(v3(o[0], o[1], o[2]), v3(o[3], o[4], o[5])); }
+
+// rigid-body inertia about the root origin, world axes: m, m r, I (xx yy zz xy xz yz)
+__device__ __forceinline__ void l_rigid10(const LBody& lb, Q4 q, V3 x, float* r10) {
+  float R[9];
+  q2mat(q, R);
+  const float* in = lb.inertia;
+  float m = lb.mass;
+  V3 r = x + mrot(R, ld3(lb.ipos));
+  float Il[9] = {in[0], in[3], in[4], in[3], in[1], in[5], in[4], in[5], in[2]}, T[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) T[3 * i + j] = R[3 * i] * Il[j] + R[3 * i + 1] * Il[3 + j] + R[3 * i + 2] * Il[6 + j];
+  float rr = dot(r, r);
+  r10[0] = m; r10[1] = m * r.x; r10[2] = m * r.y; r10[3] = m * r.z;
+  r10[4] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2] + m * (rr - r.x * r.x);
+  r10[5] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5] + m * (rr - r.y * r.y);
+  r10[6] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8] + m * (rr - r.z * r.z);
+  r10[7] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5] - m * r.x * r.y;
+  r10[8] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8] - m * r.x * r.z;
+  r10[9] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8] - m * r.y * r.z;
+}
+
+
+// ------------------------------------------------------------------ S1: outward sweep
+#define LF_GOUT 1      // stable-PD acceleration from the stored factors (FK rows of the previous forward pass) -> torque
+#define LF_FK 2        // kinematics of the state in qpos
+#define LF_VEL 4       // + velocities, bias accelerations, rigid inertias, bias forces
+#define LF_COLLIDE 8   // + floor contacts and joint-limit rows
+#define LF_SENS 16     // park framelinvel / frameangvel (quirk Q2: sensors of the last forward pass)
+#define LF_XQUAT 32    // store xquat rows (final kinematics)
+// out-mailbox of a junction body: [quat 4 | xpos 3 | - | v 6 | ab 6 | a 6]   (a: stable-PD acceleration in S1, trial acceleration in S3)
+#define LMO_Q 0
+#define LMO_X 4
+#define LMO_V 8
+#define LMO_AB 14
+#define LMO_A 20
+
+struct LFkOut { unsigned long long mask; int nrows; int dropped; };
+
+// exclusive scan of v over the 8 lanes of an env group; *total = group sum
+__device__ __forceinline__ int l_gscan(int v, const LLane& w, int* total) {
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < LM_LPE; o <<= 1) {
+    int u = __shfl_up_sync(L_FULL, inc, o);
+    if (w.li >= o) inc += u;
+  }
+  *total = __shfl_sync(L_FULL, inc, w.gbase + LM_LPE - 1);
+  return inc - v;
+}
+
+template <class C>
+__device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLane& w, int flags, bool ztau) {
+  const LHdr& H = l_hdr<C>(ms);
+  const LBody* MB = l_bodies(ms);
+  const LGeom* MG = l_geoms(ms);
+  Q4 cq; cq.w = 1.f; cq.x = cq.y = cq.z = 0.f;
+  V3 cx = v3(0.f, 0.f, 0.f);
+  S6 cv = s6(cx, cx), cab = cv, casp = cv;
+  int ncon = 0, nlim = 0, npresent = 0, dropped = 0;
+  unsigned long long gbits = 0ull;
+  const V3 pn = ld3(H.plane_n);
+  const float h0 = dot(pn, ld3(sm + C::qpos) - ld3(H.plane_pos));
+  const bool spd_torque = (flags & LF_GOUT) && H.cfg.control_mode == SMPLSIM_CTRL_UHC_PD;
+  for (int t = 0; t < H.T; t++) {
+    const int b = H.sched[t][w.li];
+    const bool actv = w.live && b >= 0;
+    float K[18], kc[3];
+    if ((flags & LF_GOUT) && !H.step_root[t]) l_rec_ld_Kc<C>(w, sm, t, b, K, kc);
+    S6 pbv = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+    float* br = sm + C::body + C::BODYW * (actv ? b : 0);
+    int alloc = 0, nlr = 0, g = 0;   // contact entries / limit rows this lane wants; its geom
+    float gd0 = 0.f, gna = 0.f, tiw0 = 0.f;
+    V3 gc = cx, gax = cx;
+    float gR[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) gR[i] = 0.f;
+    S6 vb = cv;
+    if (actv) {
+      const LBody& lb = MB[b];
+      Q4 qc; V3 x; S6 v, ab;
+      if (b == 0) {
+        // ---------------- root: free joint
+        float* qpos = sm + C::qpos;
+        const float* qvel = sm + C::qvel;
+        if (flags & LF_GOUT) {      // acceleration of the 6 root dofs from the stored factors (old rotation columns)
+          const float* rt = sm + C::root;
+          S6 a = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
+                           : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
+            float qdd = rt[36 + k] - dot6(l_arr6(rt + 6 * k), a);
+            a = a + qdd * S;
+          }
+          casp = a;
+        }
+        qc = cq; x = cx; v = cv; ab = cab;
+        if (flags & LF_FK) {
+          qc.w = qpos[3]; qc.x = qpos[4]; qc.y = qpos[5]; qc.z = qpos[6];
+          qc = qnormalize(qc);
+          qpos[3] = qc.w; qpos[4] = qc.x; qpos[5] = qc.y; qpos[6] = qc.z;
+          x = v3(0.f, 0.f, 0.f);
+          float R[9];
+          q2mat(qc, R);
+          V3 c0 = v3(R[0], R[3], R[6]), c1 = v3(R[1], R[4], R[7]), c2 = v3(R[2], R[5], R[8]);
+          st3(br + LBR_AX, c0); st3(br + LBR_AX + 3, c1); st3(br + LBR_AX + 6, c2);
+          st3(br + LBR_X, x);
+          if (flags & LF_VEL) {
+            V3 vl = ld3(qvel), wv = qvel[3] * c0 + qvel[4] * c1 + qvel[5] * c2;
+            v = s6(wv, vl);
+            ab = s6(v3(0.f, 0.f, 0.f), v3(-H.grav[0], -H.grav[1], -H.grav[2]) + cross(vl, wv));
+          }
+        }
+      } else {
+        // ---------------- hinge body
+        const int d0 = lb.dofadr;
+        if (!(lb.flags & LB_CARRY_OUT)) {   // junction: the parent's lane left its state in the mailbox
+          const float* mo = sm + C::mbo + C::MBOW * lb.pmbox;
+          cq.w = mo[LMO_Q]; cq.x = mo[LMO_Q + 1]; cq.y = mo[LMO_Q + 2]; cq.z = mo[LMO_Q + 3];
+          cx = ld3(mo + LMO_X); cv = ld6(mo + LMO_V); cab = ld6(mo + LMO_AB); casp = ld6(mo + LMO_A);
+        }
+        if (flags & LF_GOUT) {
+          // stable-PD acceleration of this body's dofs: qdd_k = c_k - K_k . a  (old joint axes / position)
+          S6 a = casp;
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            S6 S = l_hingeS(br, k);
+            float qdd = kc[k] - dot6(l_arr6(K + 6 * k), a);
+            a = a + qdd * S;
+            if (spd_torque) {      // controllers.py:165-190 with the acceleration already solved: tau = -kp (q + qd h - tgt) - kd (qd + qdd h)
+              int d = d0 + k, i = d - 6;
+              float tgt = fmaf(sm[C::act + i], lb.ascale[k], lb.aoffset[k]), q = sm[C::qpos + d + 1], qd = sm[C::qvel + d];
+              float tq = -lb.kp[k] * (q + qd * H.h - tgt) - lb.kd[k] * (qd + qdd * H.h);
+              tq = fminf(fmaxf(tq, -lb.tlim[k]), lb.tlim[k]);
+              sm[C::tau + i] = ztau ? 0.f : tq;
+            }
+          }
+          casp = a;
+        }
+        qc = cq; x = cx; v = cv; ab = cab;
+        if (flags & LF_FK) {
+          float Rp[9];
+          q2mat(cq, Rp);
+          x = cx + mrot(Rp, ld3(lb.bpos));
+          Q4 qb; qb.w = lb.bquat[0]; qb.x = lb.bquat[1]; qb.y = lb.bquat[2]; qb.z = lb.bquat[3];
+          qc = qmul(cq, qb);
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            int d = d0 + k;
+            V3 al = ld3(lb.axis + 3 * k);
+            V3 a = qrot(qc, al);
+            st3(br + LBR_AX + 3 * k, a);
+            if (flags & LF_VEL) {
+              S6 S = s6(a, cross(x, a));
+              float qd = sm[C::qvel + d];
+              ab = ab + qd * cross_motion(v, S);
+              v = v + qd * S;
+            }
+            float sn, cs;
+            l_sincos(0.5f * sm[C::qpos + d + 1], &sn, &cs);
+            Q4 qj; qj.w = cs; qj.x = al.x * sn; qj.y = al.y * sn; qj.z = al.z * sn;
+            qc = qmul(qc, qj);
+          }
+          qc = qnormalize(qc);
+          st3(br + LBR_X, x);
+        }
+      }
+      if (flags & LF_FK) {
+        if (flags & LF_VEL) {
+          float r10[10];
+          l_rigid10(lb, qc, x, r10);
+#pragma unroll
+          for (int j = 0; j < 10; j++) br[LBR_R10 + j] = r10[j];
+          pbv = rb_mul(r10, ab) + cross_force(v, rb_mul(r10, v));
+          if ((flags & LF_SENS) && w.gsens) {
+            st3(w.gsens + 6 * b, v.l + cross(v.a, x));
+            st3(w.gsens + 6 * b + 3, v.a);
+          }
+        }
+        if (flags & LF_XQUAT) { float* xq = sm + C::xq + 4 * b; xq[0] = qc.w; xq[1] = qc.x; xq[2] = qc.y; xq[3] = qc.z; }
+        cq = qc; cx = x; cv = v; cab = ab;
+      }
+      if (lb.out_mbox >= 0) {
+        float* mo = sm + C::mbo + C::MBOW * lb.out_mbox;
+        if (flags & LF_FK) {
+          mo[LMO_Q] = cq.w; mo[LMO_Q + 1] = cq.x; mo[LMO_Q + 2] = cq.y; mo[LMO_Q + 3] = cq.z;
+          st3(mo + LMO_X, cx); st6(mo + LMO_V, cv); st6(mo + LMO_AB, cab);
+        }
+        if (flags & LF_GOUT) st6(mo + LMO_A, casp);
+      }
+      vb = cv;
+      if (flags & LF_COLLIDE) {
+        // ---------------- broad phase of the body's geom: how many contact entries to reserve
+        if (lb.ngeom > 0) {
+          g = lb.geom0;
+          const LGeom& G = MG[g];
+          q2mat(cq, gR);
+          gc = cx + mrot(gR, ld3(G.pos));
+          gd0 = h0 + dot(pn, gc);
+          tiw0 = lb.tiw0;
+          if (G.type == SMPLSIM_GEOM_BOX) {
+            float ext = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; j++) ext += fabsf(dot(pn, mrot(gR, v3(G.mat[j], G.mat[3 + j], G.mat[6 + j])))) * G.size[j];
+            alloc = (gd0 - ext <= H.margin) ? 4 : 0;
+          } else {
+            gax = mrot(gR, v3(G.mat[2], G.mat[5], G.mat[8]));
+            gna = dot(pn, gax);
+            float hl = (G.type == SMPLSIM_GEOM_CAPSULE) ? G.size[1] : 0.f;
+            alloc = (gd0 - hl * fabsf(gna) - G.size[0] <= H.margin) ? ((G.type == SMPLSIM_GEOM_CAPSULE) ? 2 : 1) : 0;
+          }
+        }
+        if (b > 0) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            float q = sm[C::qpos + lb.dofadr + k + 1];
+            if (((lb.limited >> k) & 1) && (q - lb.rlo[k] < 0.f || lb.rhi[k] - q < 0.f)) nlr++;
+          }
+        }
+      }
+    }
+    if (flags & LF_VEL) l_rec_st_pb<C>(w, sm, t, b, pbv, actv);
+    if (flags & LF_COLLIDE) {
+      // ---------------- reserve list space: deterministic order (step, lane)
+      int tot, ex = l_gscan(alloc | (nlr << 8), w, &tot);
+      int cb = ncon + (ex & 255), lbs = nlim + (ex >> 8);
+      ncon += tot & 255; nlim += tot >> 8;
+      if (actv) {
+        const LBody& lb = MB[b];
+        int lcnt = nlr;
+        if (lbs + nlr > C::NLS) { lcnt = max(0, C::NLS - lbs); dropped = 1; }
+        ((int*)br)[LBR_CI] = cb | (alloc << 8) | (lbs << 16) | (lcnt << 24);
+        if (alloc) {
+          // ---------------- narrow phase (plane vs box corners / capsule ends / sphere), SURVEY A.5
+          const LGeom& G = MG[g];
+          unsigned char* pf = (unsigned char*)(sm + C::pfl);
+          V3 t1 = ld3(H.t1_default);
+          int cnt = 0;
+          const int npt = (G.type == SMPLSIM_GEOM_BOX) ? 8 : alloc;
+          if (G.type == SMPLSIM_GEOM_CAPSULE) {
+            t1 = gax - gna * pn;
+            float nn = sqrtf(dot(t1, t1));
+            t1 = (nn < 1e-15f) ? v3(1.f, 0.f, 0.f) : (1.0f / nn) * t1;
+          }
+#pragma unroll 1
+          for (int i = 0; i < npt && cnt < alloc; i++) {
+            V3 cp; float dist;
+            if (G.type == SMPLSIM_GEOM_BOX) {
+              V3 vl = v3((i & 1) ? G.size[0] : -G.size[0], (i & 2) ? G.size[1] : -G.size[1], (i & 4) ? G.size[2] : -G.size[2]);
+              V3 wv = mrot(gR, mrot(G.mat, vl));
+              float l = dot(pn, wv);
+              if (gd0 + l > H.margin || l > 0.f) continue;
+              dist = gd0 + l;
+              cp = gc + wv - (0.5f * dist) * pn;
+            } else {
+              float hl = (G.type == SMPLSIM_GEOM_CAPSULE) ? G.size[1] : 0.f, sg = i ? -hl : hl;
+              dist = gd0 + sg * gna - G.size[0];
+              if (dist > H.margin) continue;
+              cp = gc + sg * gax - (G.size[0] + 0.5f * dist) * pn;
+            }
+            float* ce = l_centry<C>(sm, w, cb + cnt);
+            float pm = dist - H.margin, imp = l_impedance(H, pm);
+            float R0 = fmaxf((1.f - imp) / imp * (tiw0 + H.mu * H.mu * tiw0), 1e-15f);
+            float R1 = R0 / fmaxf(H.impratio, 1e-15f), mu = H.mu * sqrtf(R1 / R0);
+            float kterm = H.K * imp * pm;
+            st3(ce + LCE_CP, cp); st3(ce + LCE_T1, t1);
+            ce[LCE_D] = 1.0f / (2.f * mu * mu * R0);
+#pragma unroll
+            for (int k = 0; k < 4; k++) ce[LCE_AREF + k] = -H.B * dot6(l_wrench(H, cp, t1, k), vb) - kterm;
+            // working set inherited from the slot's previous substep; new contacts start with all four rows active
+            int slot = G.slot0 + cnt, pv = pf[slot];
+            ((int*)ce)[LCE_INFO] = 1 | ((pv & 1) ? (pv & 30) : 30) | (g << 8) | (slot << 16);
+            cnt++;
+          }
+          for (int i = cnt; i < alloc; i++) ((int*)l_centry<C>(sm, w, cb + i))[LCE_INFO] = 0;
+          if (cnt) gbits |= 1ull << (g + 1);
+          npresent += cnt;
+        }
+        if (lcnt) {
+          int e = lbs;
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            int d = lb.dofadr + k;
+            float q = sm[C::qpos + d + 1], dlo = q - lb.rlo[k], dhi = lb.rhi[k] - q, dist, sg;
+            if (!((lb.limited >> k) & 1)) continue;
+            if (dlo < 0.f) { dist = dlo; sg = 1.f; }
+            else if (dhi < 0.f) { dist = dhi; sg = -1.f; }
+            else continue;
+            if (e >= lbs + lcnt) continue;
+            float* le = sm + C::lim + C::LIMW * e;
+            float imp = l_impedance(H, dist);
+            ((int*)le)[LLE_DOF] = d; le[LLE_SG] = sg;
+            le[LLE_D] = 1.0f / fmaxf((1.f - imp) / imp * lb.diw0[k], 1e-15f);
+            le[LLE_AREF] = -H.B * sg * sm[C::qvel + d] - H.K * imp * dist;
+            le[LLE_PHI] = 0.f; ((int*)le)[LLE_FLAG] = 1; le[LLE_R] = 0.f; le[LLE_RS] = 0.f;
+            e++;
+          }
+          npresent += lcnt;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  LFkOut o;
+  if (flags & LF_COLLIDE) {
+    if (w.live && w.li == 0) { ((int*)sm)[C::misc + LMI_NCON] = ncon; ((int*)sm)[C::misc + LMI_NLIM] = min(nlim, C::NLS); }
+    unsigned lo = (unsigned)(gbits & 0xffffffffull), hi = (unsigned)(gbits >> 32);
+#pragma unroll
+    for (int of = LM_LPE / 2; of > 0; of >>= 1) {
+      lo |= __shfl_xor_sync(L_FULL, lo, of); hi |= __shfl_xor_sync(L_FULL, hi, of);
+      npresent += __shfl_xor_sync(L_FULL, npresent, of); dropped |= __shfl_xor_sync(L_FULL, dropped, of);
+    }
+    o.mask = ((unsigned long long)hi << 32) | lo;
+    __syncwarp();
+  } else o.mask = 0ull;
+  o.nrows = npresent; o.dropped = dropped;
+  return o;
+}
+
+// ------------------------------------------------------------------ S2 / S4: inward sweep (articulated inertias, bias forces -> K, c)
+#define LI_SPD 1        // stable-PD system (controllers.py:165-190): D += h kd, joint force -kp e - kd qd of the state in qpos / qvel, no rows
+#define LI_INTEGRATE 2  // semi-implicit Euler of the body's own dofs first (qvel += h qacc ; qpos += h qvel), then LI_SPD on the new state
+#define LI_RESWEEP 4    // only bodies whose bit is set in st.rc_bits (chains carrying constraint rows); the other records are kept
+
+struct LSolveLane {       // lane-private sweep bookkeeping of one substep
+  unsigned dirty_bits;    // bit t: the body of step t has constraint rows in its subtree
+  unsigned rc_bits;       // bit t: the body of step t is recomputed by re-sweeps (dirty, or hands its result over in registers to such a body)
+  float dispx, dispy;     // root displacement of this substep (lane of the root body)
+};
+
+template <class C>
+__device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane& w, bool run, int flags, LSolveLane& st) {
+  const LHdr& H = l_hdr<C>(ms);
+  const LBody* MB = l_bodies(ms);
+  float cA[21];
+#pragma unroll
+  for (int j = 0; j < 21; j++) cA[j] = 0.f;
+  S6 cp = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+  bool cdirty = false;
+  const bool spd = (flags & LI_SPD) != 0, resweep = (flags & LI_RESWEEP) != 0;
+  if (!resweep && !spd) st.dirty_bits = 0u;
+  for (int t = H.T - 1; t >= 0; t--) {
+    const int b = H.sched[t][w.li];
+    const bool actv = run && b >= 0;
+    const bool need = actv && (!resweep || ((st.rc_bits >> t) & 1u));
+    if (resweep && !__any_sync(L_FULL, need)) continue;
+    S6 p = l_rec_ld_pb<C>(w, sm, t, b);
+    float K[18], kc[3];
+#pragma unroll
+    for (int j = 0; j < 18; j++) K[j] = 0.f;
+    kc[0] = kc[1] = kc[2] = 0.f;
+    if (need) {
+      const LBody& lb = MB[b];
+      float* br = sm + C::body + C::BODYW * b;
+      float A[21];
+      rb_expand(br + LBR_R10, A);
+      bool dirty = false;
+      if (lb.flags & LB_CARRY_IN) {
+#pragma unroll
+        for (int j = 0; j < 21; j++) A[j] += cA[j];
+        p = p + cp; dirty = cdirty;
+      }
+      for (int j = 0; j < lb.nmb; j++) {
+        const float* mi = sm + C::mbi + C::MBIW * lb.mb[j];
+#pragma unroll
+        for (int i = 0; i < 21; i++) A[i] += mi[i];
+        p = p + ld6(mi + 21);
+        dirty = dirty || (((const int*)mi)[27] != 0);
+      }
+      float lD[3] = {0.f, 0.f, 0.f}, lT[3] = {0.f, 0.f, 0.f};
+      if (!spd) {
+        const int ci = ((const int*)br)[LBR_CI], cb = ci & 255, cn = (ci >> 8) & 255, lbs = (ci >> 16) & 255, ln = (ci >> 24) & 255;
+        dirty = dirty || cn > 0 || ln > 0;
+        for (int c = cb; c < cb + cn; c++) {
+          const float* ce = l_centry<C>(sm, w, c);
+          int info = ((const int*)ce)[LCE_INFO];
+          if (!(info & 1) || !(info & 30)) continue;
+          V3 cpt = ld3(ce + LCE_CP), t1 = ld3(ce + LCE_T1);
+          float D = ce[LCE_D];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (!(info & (2 << k))) continue;
+            S6 xw = l_wrench(H, cpt, t1, k);
+            float xv[6];
+            l_s6arr(xw, xv);
+            sym_rank1(A, xv, -D);
+            p = p - (D * ce[LCE_AREF + k]) * xw;
+          }
+        }
+        for (int e = lbs; e < lbs + ln; e++) {   // joint-limit rows of this body that sit in the working set
+          const float* le = sm + C::lim + C::LIMW * e;
+          if (!(((const int*)le)[LLE_FLAG] & 1)) continue;
+          int k = ((const int*)le)[LLE_DOF] - lb.dofadr;
+#pragma unroll
+          for (int kk = 0; kk < 3; kk++) if (kk == k) { lD[kk] = le[LLE_D]; lT[kk] = le[LLE_SG] * le[LLE_D] * le[LLE_AREF]; }
+        }
+      }
+      if (b == 0) {
+        // ---------------- root: six free-joint dofs, factors kept in shared memory
+        float* rt = sm + C::root;
+        if (flags & LI_INTEGRATE) {
+          float* qpos = sm + C::qpos; float* qvel = sm + C::qvel; const float* qacc = sm + C::qacc;
+          float h = H.h;
+#pragma unroll
+          for (int d = 0; d < 6; d++) {
+            float v = fmaf(h, qacc[d], qvel[d]);
+            qvel[d] = v;
+            if (d < 3) { float dd = h * v; qpos[d] += dd; if (d == 0) st.dispx += dd; if (d == 1) st.dispy += dd; }
+          }
+          V3 wv = ld3(qvel + 3);
+          float n = sqrtf(dot(wv, wv)), ang = n * h;
+          Q4 q; q.w = qpos[3]; q.x = qpos[4]; q.y = qpos[5]; q.z = qpos[6];
+          if (ang > 0.f) {
+            float sn, cs;
+            l_sincos(0.5f * ang, &sn, &cs);
+            float s = sn / n;
+            Q4 dq; dq.w = cs; dq.x = wv.x * s; dq.y = wv.y * s; dq.z = wv.z * s;
+            q = qmul(q, dq);
+          }
+          q = qnormalize(q);
+          qpos[3] = q.w; qpos[4] = q.x; qpos[5] = q.y; qpos[6] = q.z;
+        }
+#pragma unroll
+        for (int k = 5; k >= 0; k--) {
+          S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
+                         : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
+          float s[6], Uv[6];
+          l_s6arr(S, s);
+          sym_mul(A, s, Uv);
+          float D = H.rarm[k];
+#pragma unroll
+          for (int j = 0; j < 6; j++) D = fmaf(s[j], Uv[j], D);
+          float di = 1.0f / D;
+          float uu = -dot6(S, p);
+          sym_rank1(A, Uv, di);
+          p = p + (uu * di) * l_arr6(Uv);
+#pragma unroll
+          for (int j = 0; j < 6; j++) rt[6 * k + j] = Uv[j] * di;
+          rt[36 + k] = uu * di;
+        }
+      } else {
+        // ---------------- hinge body: three dofs, last joint first
+        const int d0 = lb.dofadr;
+#pragma unroll
+        for (int k = 2; k >= 0; k--) {
+          const int d = d0 + k, i = d - 6;
+          S6 S = l_hingeS(br, k);
+          float s[6], Uv[6];
+          l_s6arr(S, s);
+          sym_mul(A, s, Uv);
+          float D = lb.arm[k] + (spd ? H.h * lb.kd[k] : lD[k]);
+#pragma unroll
+          for (int j = 0; j < 6; j++) D = fmaf(s[j], Uv[j], D);
+          float di = 1.0f / D, tin;
+          if (spd) {
+            float q = sm[C::qpos + d + 1], qd = sm[C::qvel + d];
+            if (flags & LI_INTEGRATE) {
+              qd = fmaf(H.h, sm[C::qacc + d], qd); q = fmaf(H.h, qd, q);
+              sm[C::qvel + d] = qd; sm[C::qpos + d + 1] = q;
+            }
+            float tgt = fmaf(sm[C::act + i], lb.ascale[k], lb.aoffset[k]);
+            tin = -lb.kp[k] * (q + qd * H.h - tgt) - lb.kd[k] * qd;
+          } else tin = sm[C::tau + i] + lT[k];
+          float uu = tin - dot6(S, p);
+          sym_rank1(A, Uv, di);
+          p = p + (uu * di) * l_arr6(Uv);
+#pragma unroll
+          for (int j = 0; j < 6; j++) K[6 * k + j] = Uv[j] * di;
+          kc[k] = uu * di;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 21; j++) cA[j] = A[j];
+      cp = p; cdirty = dirty;
+      if (lb.in_mbox >= 0) {
+        float* mi = sm + C::mbi + C::MBIW * lb.in_mbox;
+#pragma unroll
+        for (int j = 0; j < 21; j++) mi[j] = A[j];
+        st6(mi + 21, p);
+        ((int*)mi)[27] = dirty ? 1 : 0;
+      }
+      if (!spd && !resweep && dirty) st.dirty_bits |= 1u << t;
+    }
+    if (!H.step_root[t]) l_rec_st_Kc<C>(w, sm, t, b, K, kc, need && b > 0, resweep);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ S3: outward sweep of the accelerations + residuals of the constraint rows
+// qdd -> qacc (no iterate yet) or qstar (trial point of the line search); rs = J a - aref of every row; returns "the sign pattern
+// of the rows equals the working set" for this lane's env.  first: also derive rc_bits from dirty_bits.
+template <class C>
+__device__ __noinline__ bool l_sweep_acc(const float* ms, float* sm, const LLane& w, bool run, bool to_qstar, bool first, LSolveLane& st) {
+  const LHdr& H = l_hdr<C>(ms);
+  const LBody* MB = l_bodies(ms);
+  S6 ca = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+  bool crc = false, same = true;
+  float* qout = sm + (to_qstar ? C::qstar : C::qacc);
+  if (first) st.rc_bits = 0u;
+  for (int t = 0; t < H.T; t++) {
+    const int b = H.sched[t][w.li];
+    const bool actv = run && b >= 0;
+    float K[18], kc[3];
+    if (!H.step_root[t]) l_rec_ld_Kc<C>(w, sm, t, b, K, kc);
+    if (actv) {
+      const LBody& lb = MB[b];
+      const float* br = sm + C::body + C::BODYW * b;
+      S6 a;
+      float qdd3[3] = {0.f, 0.f, 0.f};
+      if (b == 0) {
+        const float* rt = sm + C::root;
+        a = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
+                         : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
+          float qdd = rt[36 + k] - dot6(l_arr6(rt + 6 * k), a);
+          qout[k] = qdd;
+          a = a + qdd * S;
+        }
+        crc = false;
+      } else {
+        if (!(lb.flags & LB_CARRY_OUT)) { ca = ld6(sm + C::mbo + C::MBOW * lb.pmbox + LMO_A); crc = false; }
+        a = ca;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          S6 S = l_hingeS(br, k);
+          float qdd = kc[k] - dot6(l_arr6(K + 6 * k), a);
+          qout[lb.dofadr + k] = qdd;
+          qdd3[k] = qdd;
+          a = a + qdd * S;
+        }
+      }
+      ca = a;
+      if (lb.out_mbox >= 0) st6(sm + C::mbo + C::MBOW * lb.out_mbox + LMO_A, a);
+      const int ci = ((const int*)br)[LBR_CI], cb = ci & 255, cn = (ci >> 8) & 255, lbs = (ci >> 16) & 255, ln = (ci >> 24) & 255;
+      for (int c = cb; c < cb + cn; c++) {
+        float* ce = l_centry<C>(sm, w, c);
+        int info = ((const int*)ce)[LCE_INFO];
+        if (!(info & 1)) continue;
+        V3 cpt = ld3(ce + LCE_CP), t1 = ld3(ce + LCE_T1);
+        int nf = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          float rs = dot6(l_wrench(H, cpt, t1, k), a) - ce[LCE_AREF + k];
+          ce[LCE_RS + k] = rs;
+          if (rs < 0.f) nf |= 2 << k;
+        }
+        if (nf != (info & 30)) same = false;
+      }
+      for (int e = lbs; e < lbs + ln; e++) {
+        float* le = sm + C::lim + C::LIMW * e;
+        int k = ((const int*)le)[LLE_DOF] - lb.dofadr;
+        float qd = (k == 0) ? qdd3[0] : (k == 1) ? qdd3[1] : qdd3[2];
+        float rs = le[LLE_SG] * qd - le[LLE_AREF];
+        le[LLE_RS] = rs;
+        if ((rs < 0.f ? 1 : 0) != (((const int*)le)[LLE_FLAG] & 1)) same = false;
+      }
+      if (first) {
+        bool rc = ((st.dirty_bits >> t) & 1u) || ((lb.flags & LB_CARRY_OUT) && crc);
+        crc = rc;
+        if (rc) st.rc_bits |= 1u << t;
+      }
+    }
+    __syncwarp();
+  }
+  return l_gall(same || !run, w);
+}
+
+// ------------------------------------------------------------------ row-space passes of the exact line search (lane-parallel over the row lists)
+// r = J a - aref at the iterate, rs at the trial point, d = rs - r; phi: force of the row at the iterate.
+// op 0: adopt  (phi := -D rs on the working set ; set := rs < 0 ; r := rs)
+// op 1: sums   (g1 += d phi ; g2 += d (phis - phi) ; s1, s2 at step al)
+// op 2: apply  (phi += al (phis - phi) ; r += al d ; set := (r < 0))
+// op 3: take   (set unchanged at the trial point: r := rs, phi := -D rs on the set)        [fin with an iterate: bookkeeping only]
+template <class C>
+__device__ __noinline__ void l_rows(float* sm, const LLane& w, bool run, int op, float al, float* out4) {
+  float g1 = 0.f, g2 = 0.f, s1 = 0.f, s2 = 0.f;
+  if (run) {
+    const int ncon = ((const int*)sm)[C::misc + LMI_NCON], nlim = ((const int*)sm)[C::misc + LMI_NLIM];
+    for (int c = w.li; c < ncon; c += LM_LPE) {
+      float* ce = l_centry<C>(sm, w, c);
+      int info = ((int*)ce)[LCE_INFO];
+      if (!(info & 1)) continue;
+      float D = ce[LCE_D];
+      int nf = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        float rs = ce[LCE_RS + k], phs = (info & (2 << k)) ? -D * rs : 0.f;
+        if (op == 0) { ce[LCE_PHI + k] = phs; ce[LCE_R + k] = rs; if (rs < 0.f) nf |= 2 << k; }
+        else {
+          float r = ce[LCE_R + k], d = rs - r, ph = ce[LCE_PHI + k], v = fmaf(al, d, r);
+          if (op == 1) {
+            g1 = fmaf(d, ph, g1); g2 = fmaf(d, phs - ph, g2);
+            if (v < 0.f) { s1 = fmaf(D * v, d, s1); s2 = fmaf(D * d, d, s2); }
+          } else { ce[LCE_PHI + k] = fmaf(al, phs - ph, ph); ce[LCE_R + k] = v; if (v < 0.f) nf |= 2 << k; }
+        }
+      }
+      if (op != 1) ((int*)ce)[LCE_INFO] = (info & ~30) | nf;
+    }
+    for (int e = w.li; e < nlim; e += LM_LPE) {
+      float* le = sm + C::lim + C::LIMW * e;
+      int fl = ((int*)le)[LLE_FLAG];
+      float D = le[LLE_D], rs = le[LLE_RS], phs = (fl & 1) ? -D * rs : 0.f;
+      if (op == 0) { le[LLE_PHI] = phs; le[LLE_R] = rs; ((int*)le)[LLE_FLAG] = rs < 0.f ? 1 : 0; }
+      else {
+        float r = le[LLE_R], d = rs - r, ph = le[LLE_PHI], v = fmaf(al, d, r);
+        if (op == 1) {
+          g1 = fmaf(d, ph, g1); g2 = fmaf(d, phs - ph, g2);
+          if (v < 0.f) { s1 = fmaf(D * v, d, s1); s2 = fmaf(D * d, d, s2); }
+        } else { le[LLE_PHI] = fmaf(al, phs - ph, ph); le[LLE_R] = v; ((int*)le)[LLE_FLAG] = v < 0.f ? 1 : 0; }
+      }
+    }
+  }
+  out4[0] = g1; out4[1] = g2; out4[2] = s1; out4[3] = s2;
+}
+
+// ------------------------------------------------------------------ constraint solve: active-set Newton, every system one ABA pass
+// Returns the number of extra solves; *hit_max: stopped at L_SOLVER_MAXITER.
+template <class C>
+__device__ __noinline__ int l_solve(const float* ms, float* sm, const LLane& w, bool any_rows, LSolveLane& st, bool* hit_max) {
+  const LHdr& H = l_hdr<C>(ms);
+  // first pass for every live env: the working set inherited from the previous substep is already in the row lists
+  l_sweep_in<C>(ms, sm, w, w.live, 0, st);
+  bool same0 = l_sweep_acc<C>(ms, sm, w, w.live, false, true, st);   // qdd -> qacc
+  bool run = w.live && any_rows && !same0;
+  *hit_max = false;
+  if (!__any_sync(L_FULL, run)) return 0;
+  // envs whose first trial point changed the sign pattern: adopt it as the iterate, then iterate
+  float o4[4];
+  l_rows<C>(sm, w, run, 0, 0.f, o4);
+  __syncwarp();
+  int it = 1, iters = 0;
+  for (; it < L_SOLVER_MAXITER; it++) {
+    if (!__any_sync(L_FULL, run)) break;
+    l_sweep_in<C>(ms, sm, w, run, H.dirtypath ? LI_RESWEEP : 0, st);
+    bool same = l_sweep_acc<C>(ms, sm, w, run, true, false, st);      // qdd -> qstar
+    bool fin = run && same, lsrch = run && !same;
+    if (__any_sync(L_FULL, lsrch)) {   // exact line search between the iterate (qacc, r, phi) and the trial point (qstar, rs), row space only
+      l_rows<C>(sm, w, lsrch, 1, 0.f, o4);
+      float g1 = l_gsum(o4[0]), g2 = l_gsum(o4[1]), s1 = l_gsum(o4[2]), s2;
+      float f0 = g1 + s1, al = 0.f, lo = 0.f, hi = -1.f, tol = H.ls_tol * fabsf(f0);
+      bool searching = lsrch && (f0 < -L_LS_NOISE * (fabsf(g1) + fabsf(s1)));   // |f0| below the fp32 cancellation floor: converged
+      if (searching) al = 1.f;
+      for (int ls = 0; ls < L_LS_MAXITER; ls++) {
+        if (!__any_sync(L_FULL, searching)) break;
+        l_rows<C>(sm, w, searching, 1, al, o4);
+        s1 = l_gsum(o4[2]); s2 = l_gsum(o4[3]);
+        if (searching) {
+          float f = g1 + al * g2 + s1, fp = g2 + s2;
+          if (fabsf(f) <= tol) searching = false;
+          else {
+            if (f < 0.f) lo = al; else hi = al;
+            float an = (fp > 0.f) ? al - f / fp : -1.f;
+            if (!(an > lo) || (hi > 0.f && !(an < hi))) an = (hi > 0.f) ? 0.5f * (lo + hi) : 2.f * al;
+            an = fminf(an, L_LS_MAXSTEP);
+            if (an == al) searching = false; else al = an;
+          }
+        }
+      }
+      bool step = lsrch && (al > 0.f);
+      if (lsrch && !step) { run = false; iters = it; }
+      l_rows<C>(sm, w, step, 2, al, o4);
+      if (step) for (int d = w.li; d < H.nv; d += LM_LPE) sm[C::qacc + d] = fmaf(al, sm[C::qstar + d] - sm[C::qacc + d], sm[C::qacc + d]);
+    }
+    if (fin) {
+      for (int d = w.li; d < H.nv; d += LM_LPE) sm[C::qacc + d] = sm[C::qstar + d];
+      run = false; iters = it;
+    }
+    __syncwarp();
+  }
+  if (run) { iters = it; *hit_max = true; }
+  return iters;
+}
+
+// ------------------------------------------------------------------ elementwise controllers (pd / torque / simple_pid), controllers.py:6-47,186-349
+template <class C>
+__device__ __noinline__ void l_torque_elem(const float* ms, float* sm, const LLane& w, const SmplsimState& sta) {
+  const LHdr& H = l_hdr<C>(ms);
+  const LBody* MB = l_bodies(ms);
+  const int mode = H.cfg.control_mode;
+  if (w.live) {
+    for (int i = w.li; i < H.nu; i += LM_LPE) {
+      const int b = 1 + i / 3, k = i - 3 * (b - 1);     // SMPL family: three hinges per non-root body, dofs in body order
+      const LBody& lb = MB[b];
+      float a = sm[C::act + i], tq;
+      if (mode == SMPLSIM_CTRL_TORQUE) tq = a * lb.ascale[k];
+      else if (mode == SMPLSIM_CTRL_SIMPLE_PID) {   // stateful: integral / last error live in HBM (L2-resident, 2 x nu words per env)
+        size_t o = (size_t)w.env * H.nu + i;
+        float dt = H.h * (float)H.cfg.nsubsteps, lim = lb.tlim[k];
+        float err = fmaf(a, lb.ascale[k], lb.aoffset[k]) - sm[C::qpos + 7 + i], le = sta.pid_last_error[o];
+        float derr = (le != le) ? 0.f : err - le;
+        float in = fminf(fmaxf(fmaf(err, dt, sta.pid_integral[o]), -lim), lim);
+        sta.pid_integral[o] = in; sta.pid_last_error[o] = err;
+        tq = lb.kp[k] * err + in + lb.kd[k] * derr / dt;
+      } else {
+        float tgt = fmaf(a, lb.ascale[k], lb.aoffset[k]), q = sm[C::qpos + 7 + i], qd = sm[C::qvel + 6 + i];
+        tq = -lb.kp[k] * (q - tgt) - lb.kd[k] * qd;
+      }
+      sm[C::tau + i] = fminf(fmaxf(tq, -lb.tlim[k]), lb.tlim[k]);
+    }
+  }
+  __syncwarp();
+}
+
+// semi-implicit Euler when no stable-PD sweep follows (elementwise; root quaternion by the first lane)
+template <class C>
+__device__ __noinline__ void l_integrate(const float* ms, float* sm, const LLane& w, LSolveLane& st) {
+  const LHdr& H = l_hdr<C>(ms);
+  if (w.live) {
+    float h = H.h;
+    for (int d = 3 + w.li; d < H.nv; d += LM_LPE) {
+      float v = fmaf(h, sm[C::qacc + d], sm[C::qvel + d]);
+      sm[C::qvel + d] = v;
+      if (d >= 6) sm[C::qpos + d + 1] = fmaf(h, v, sm[C::qpos + d + 1]);
+    }
+    if (w.li == 0) {   // root translation on the lane that keeps the displacement
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        float v = fmaf(h, sm[C::qacc + d], sm[C::qvel + d]), dd = h * v;
+        sm[C::qvel + d] = v; sm[C::qpos + d] += dd;
+        if (d == 0) st.dispx += dd;
+        if (d == 1) st.dispy += dd;
+      }
+    }
+  }
+  __syncwarp();
+  if (w.live && w.li == 0) {
+    float* qpos = sm + C::qpos;
+    V3 wv = ld3(sm + C::qvel + 3);
+    float n = sqrtf(dot(wv, wv)), ang = n * H.h;
+    Q4 q; q.w = qpos[3]; q.x = qpos[4]; q.y = qpos[5]; q.z = qpos[6];
+    if (ang > 0.f) {
+      float sn, cs;
+      l_sincos(0.5f * ang, &sn, &cs);
+      float s = sn / n;
+      Q4 dq; dq.w = cs; dq.x = wv.x * s; dq.y = wv.y * s; dq.z = wv.z * s;
+      q = qmul(q, dq);
+    }
+    q = qnormalize(q);
+    qpos[3] = q.w; qpos[4] = q.x; qpos[5] = q.y; qpos[6] = q.z;
+  }
+  __syncwarp();
+}
+
+// mj_checkPos / mj_checkVel (what 0, before the forward pass) and mj_checkAcc (what 1, after the solve), SURVEY A.2
+// ([MJ-upstream] engine_forward.c): a NaN or |x| > mjMAXVAL raises the warning bit and auto-resets the env's data like
+// mj_resetData (qpos = qpos0, qvel = ctrl = qacc_warmstart = 0).  Returns the warning bits of this lane's env.
+template <class C>
+__device__ __noinline__ int l_check(const float* ms, float* sm, const LLane& w, int what) {
+  const LHdr& H = l_hdr<C>(ms);
+  bool b0 = false, b1 = false;
+  if (w.live) {
+    if (what == 0) {
+#pragma unroll 1
+      for (int i = w.li; i < H.nv + 1; i += LM_LPE) b0 |= !(fabsf(sm[C::qpos + i]) <= L_MAXVAL);
+#pragma unroll 1
+      for (int i = w.li; i < H.nv; i += LM_LPE) b1 |= !(fabsf(sm[C::qvel + i]) <= L_MAXVAL);
+    } else {
+#pragma unroll 1
+      for (int i = w.li; i < H.nv; i += LM_LPE) b0 |= !(fabsf(sm[C::qacc + i]) <= L_MAXVAL);
+    }
+  }
+  b0 = l_gany(b0, w); b1 = l_gany(b1, w);
+  int bits = (what == 0) ? (b0 ? 1 : (b1 ? 2 : 0)) : (b0 ? 4 : 0);
+  if (bits && w.live) {
+    const LBody* MB = l_bodies(ms);
+#pragma unroll 1
+    for (int i = w.li; i < H.nv + 1; i += LM_LPE) sm[C::qpos + i] = (i < 3) ? MB[0].bpos[i] : (i < 7) ? MB[0].bquat[i - 3] : 0.f;
+#pragma unroll 1
+    for (int i = w.li; i < H.nv; i += LM_LPE) { sm[C::qvel + i] = 0.f; sm[C::qacc + i] = 0.f; }
+#pragma unroll 1
+    for (int i = w.li; i < H.nu; i += LM_LPE) sm[C::tau + i] = 0.f;
+  }
+  __syncwarp();
+  return bits;
+}
+
+// the slot -> working-set memory the next substep's contacts inherit from
+template <class C>
+__device__ __forceinline__ void l_save_working_set(const float* ms, float* sm, const LLane& w) {
+  const LHdr& H = l_hdr<C>(ms);
+  if (w.live) for (int i = w.li; i < (H.nslot + 3) / 4; i += LM_LPE) ((int*)sm)[C::pfl + i] = 0;
+  __syncwarp();
+  if (w.live) {
+    unsigned char* pf = (unsigned char*)(sm + C::pfl);
+    const int ncon = ((const int*)sm)[C::misc + LMI_NCON];
+    for (int c = w.li; c < ncon; c += LM_LPE) {
+      int info = ((const int*)l_centry<C>(sm, w, c))[LCE_INFO];
+      if (info & 1) pf[(info >> 16) & 255] = (unsigned char)(info & 31);
+    }
+  }
+  __syncwarp();
+}
+
+struct LFwd { unsigned long long mask; int iters; int status; };
+
+// ------------------------------------------------------------------ nsub x [compute_torque + mj_step]   (humanoid_env.py:439-453)
+// Entry condition in stable-PD (stale) mode: records hold the (M + h Kd) factors of the last forward pass for the state in
+// qpos / qvel and the action in act (prologue of the kernels: l_spd_prologue).
+template <class C>
+__device__ __noinline__ void l_substeps(const float* ms, float* sm, const LLane& w, int nsub, int raw, LFwd* fo, const SmplsimState& sta,
+                                        bool write_fwd, bool prep_last, LSolveLane& st) {
+  const LHdr& H = l_hdr<C>(ms);
+  const bool spd = (H.cfg.control_mode == SMPLSIM_CTRL_UHC_PD) && !raw, stale = H.cfg.spd_stale != 0;
+  bool restore = false;   // raw mode: the caller's ctrl (kept in act) comes back the substep after an auto-reset zeroed it
+  for (int s = 0; s < nsub; s++) {
+    if (!raw) {
+      if (!spd) l_torque_elem<C>(ms, sm, w, sta);
+    } else if (__any_sync(L_FULL, restore)) {
+      if (w.live && restore) for (int i = w.li; i < H.nu; i += LM_LPE) sm[C::tau + i] = sm[C::act + i];
+      restore = false;
+      __syncwarp();
+    }
+    int bad = l_check<C>(ms, sm, w, 0);
+    if (spd && !stale) {   // spd_inertia = "fresh": factors of the current state, then the torque
+      l_sweep_out<C>(ms, sm, w, LF_FK | LF_VEL, false);
+      l_sweep_in<C>(ms, sm, w, w.live, LI_SPD, st);
+      l_sweep_out<C>(ms, sm, w, LF_GOUT, bad != 0);
+    }
+    const bool last = (s == nsub - 1);
+    int f1 = LF_FK | LF_VEL | LF_COLLIDE | ((spd && stale) ? LF_GOUT : 0) | (last ? LF_SENS : 0);
+    LFkOut fk = l_sweep_out<C>(ms, sm, w, f1, bad != 0);
+    bool hit = false;
+    fo->mask = fk.mask;
+    fo->iters = l_solve<C>(ms, sm, w, fk.nrows > 0, st, &hit);
+    int extra = (fk.dropped ? L_ST_ROWS_DROPPED : 0) | (hit ? L_ST_MAXITER : 0);
+    int badacc = l_check<C>(ms, sm, w, 1);
+    if (__any_sync(L_FULL, badacc != 0)) {   // mj_checkAcc: forward pass again on the reset data, then integrate
+      LLane w2 = w;
+      w2.live = w.live && badacc != 0;
+      LFkOut fk2 = l_sweep_out<C>(ms, sm, w2, LF_FK | LF_VEL | LF_COLLIDE | (last ? LF_SENS : 0), false);
+      bool hit2 = false;
+      int it2 = l_solve<C>(ms, sm, w2, fk2.nrows > 0, st, &hit2);
+      if (badacc) { fo->mask = fk2.mask; fo->iters = it2; }
+    }
+    l_save_working_set<C>(ms, sm, w);
+    bad |= badacc;
+    fo->status |= bad | extra;
+    if (raw && bad) restore = true;
+    if (last && write_fwd && w.live) {
+      float* qf = sta.qpos_fwd + (size_t)w.env * (H.nv + 1); float* vf = sta.qvel_fwd + (size_t)w.env * H.nv;
+      for (int i = w.li; i < H.nv + 1; i += LM_LPE) qf[i] = sm[C::qpos + i];
+      for (int i = w.li; i < H.nv; i += LM_LPE) vf[i] = sm[C::qvel + i];
+    }
+    if (last && write_fwd) __syncwarp();   // the integration below overwrites what other lanes are still copying
+    if (spd && stale && (!last || prep_last)) l_sweep_in<C>(ms, sm, w, w.live, LI_SPD | LI_INTEGRATE, st);   // FK rows: s_k ; qpos / qvel: s_{k+1}
+    else l_integrate<C>(ms, sm, w, st);
+  }
+}
+
+// ====================================================================================================================
+// env-level kernels
+// ====================================================================================================================
+struct LStepArgs {
+  SmplsimState st;
+  SmplsimAux aux;
+  const float* action;
+  float* obs;
+  float* reward;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  float* gscr;       // [n, (NS - NCS) * CONW] overflow contact entries
+  float* gsens;      // [n, 6 nb] or NULL
+  int n, nsub, mode;
+};
+struct LResetArgs {
+  SmplsimState st;
+  SmplsimAux aux;
+  const uint8_t* mask;
+  const float* qpos0;
+  const float* qvel0;
+  float* obs;
+  float* gscr;
+  float* gsens;
+  int n, init_mode;
+};
+struct LKinArgs { const float* qpos; float* xpos; float* xquat; int n; };
+
+template <class C>
+__device__ __forceinline__ void l_copy(float* dst, const float* src, int n, const LLane& w) {
+  if (w.live) for (int i = w.li; i < n; i += LM_LPE) dst[i] = src[i];
+}
+// rows whose length and base are multiples of 4 words move as float4 (state rows are padded to 16 bytes only in shared memory,
+// so the global side is checked at run time)
+template <class C>
+__device__ __forceinline__ void l_copy_in(float* dst, const float* __restrict__ src, int n, const LLane& w) {
+  if (!w.live) return;
+  if ((((size_t)src) & 15) == 0) {
+    int n4 = n >> 2;
+    for (int i = w.li; i < n4; i += LM_LPE) ((float4*)dst)[i] = ((const float4*)src)[i];
+    for (int i = (n4 << 2) + w.li; i < n; i += LM_LPE) dst[i] = src[i];
+  } else for (int i = w.li; i < n; i += LM_LPE) dst[i] = src[i];
+}
+template <class C>
+__device__ __forceinline__ void l_copy_out(float* __restrict__ dst, const float* src, int n, const LLane& w) {
+  if (!w.live) return;
+  if ((((size_t)dst) & 15) == 0) {
+    int n4 = n >> 2;
+    for (int i = w.li; i < n4; i += LM_LPE) ((float4*)dst)[i] = ((const float4*)src)[i];
+    for (int i = (n4 << 2) + w.li; i < n; i += LM_LPE) dst[i] = src[i];
+  } else for (int i = w.li; i < n; i += LM_LPE) dst[i] = src[i];
+}
+
+template <class C>
+__device__ __noinline__ void l_task_io(float* sm, const LLane& w, const SmplsimState& st, bool store) {
+  if (store) __syncwarp();
+  if (w.live && w.li == 0) {
+    float* t = sm + C::tsk;
+    int* ti = (int*)t;
+    int env = w.env;
+    if (!store) {
+      for (int j = 0; j < 4; j++) t[j] = st.task_target[4 * env + j];
+      ti[L_TSK_CHANGE] = st.task_change_step[env]; ti[L_TSK_CURT] = st.progress[env]; ti[L_TSK_RECOV] = st.recovery[env];
+      ti[L_TSK_RNG] = (int)st.rng_counter[env];
+    } else {
+      for (int j = 0; j < 4; j++) st.task_target[4 * env + j] = t[j];
+      st.task_change_step[env] = ti[L_TSK_CHANGE]; st.progress[env] = ti[L_TSK_CURT]; st.recovery[env] = ti[L_TSK_RECOV];
+      st.rng_counter[env] = (uint32_t)ti[L_TSK_RNG];
+    }
+  }
+  if (!store) __syncwarp();
+}
+
+// reset_task() of the three tasks (tasks/humanoid_speed.py:97-103, humanoid_reach.py:80-90, humanoid_getup.py:83-89); first lane only
+template <class C>
+__device__ __noinline__ void l_reset_task(const LHdr& H, float* sm, int env) {
+  const SmplsimEnvCfg& c = H.cfg;
+  if (c.task == SMPLSIM_TASK_NONE) return;
+  float* t = sm + C::tsk;
+  int* ti = (int*)t;
+  uint32_t r[4];
+  philox4x32((uint32_t)ti[L_TSK_RNG], (uint32_t)env, 0u, 0u, (uint32_t)c.seed, (uint32_t)(c.seed >> 32), r);
+  ti[L_TSK_RNG] = ti[L_TSK_RNG] + 1;
+  if (c.task == SMPLSIM_TASK_SPEED) t[0] = (float)(c.tar_speed_max - c.tar_speed_min) * u01(r[0]) + (float)c.tar_speed_min;
+  else if (c.task == SMPLSIM_TASK_REACH) {
+    t[0] = (float)c.tar_dist_max * (2.0f * u01(r[0]) - 1.0f);
+    t[1] = (float)c.tar_dist_max * (2.0f * u01(r[1]) - 1.0f);
+    t[2] = (float)(c.tar_height_max - c.tar_height_min) * u01(r[2]) + (float)c.tar_height_min;
+  } else t[0] = (float)(c.tar_height_max - c.tar_height_min) * u01(r[0]) + (float)c.tar_height_min;
+  ti[L_TSK_CHANGE] = ti[L_TSK_CURT] + rand_range(r[3], c.change_steps_min, c.change_steps_max);
+}
+
+__device__ __forceinline__ Q4 l_heading_inv(const LHdr& H, Q4 root) {
+  if (!H.cfg.upright_start) { Q4 bc; bc.w = 0.5f; bc.x = -0.5f; bc.y = -0.5f; bc.z = -0.5f; root = qmul(root, bc); }
+  V3 rd = qrot_ref(root, v3(1.f, 0.f, 0.f));
+  float hd = atan2f(rd.y, rd.x), sn, cs;
+  l_sincos(-0.5f * hd, &sn, &cs);
+  Q4 h; h.w = cs; h.x = 0.f; h.y = 0.f; h.z = sn;
+  return qnormalize(h);
+}
+
+// compute_observations (humanoid_env.py:565-688, tasks/*.py): staged in shared memory, then streamed out coalesced
+template <class C>
+__device__ __noinline__ void l_write_obs(const float* ms, float* sm, const LLane& w, float* obs_row) {
+  const LHdr& H = l_hdr<C>(ms);
+  if (w.live) {
+    float* ob = sm + C::obs;
+    const float *qpos = sm + C::qpos, *xq = sm + C::xq, *qvel = sm + C::qvel, *sens = w.gsens;
+    int nb = H.nb;
+    Q4 r0; r0.w = xq[0]; r0.x = xq[1]; r0.y = xq[2]; r0.z = xq[3];
+    Q4 hq = l_heading_inv(H, r0);
+    int o = H.cfg.root_height_obs ? 1 : 0, o_rot = o + 3 * (nb - 1), o_vel = o_rot + 6 * nb;
+    if (o && w.li == 0) ob[0] = qpos[2];
+    for (int b = w.li; b < nb; b += LM_LPE) {
+      if (b > 0) st3(ob + o + 3 * (b - 1), qrot_ref(hq, ld3(sm + C::body + C::BODYW * b + LBR_X)));
+      Q4 q; q.w = xq[4 * b]; q.x = xq[4 * b + 1]; q.y = xq[4 * b + 2]; q.z = xq[4 * b + 3];
+      Q4 lq = qmul(hq, q);
+      st3(ob + o_rot + 6 * b, qrot_ref(lq, v3(1.f, 0.f, 0.f)));
+      st3(ob + o_rot + 6 * b + 3, qrot_ref(lq, v3(0.f, 0.f, 1.f)));
+      if (H.cfg.self_obs_v == 2 && sens) {
+        st3(ob + o_vel + 3 * b, qrot_ref(hq, ld3(sens + 6 * b)));
+        st3(ob + o_vel + 3 * nb + 3 * b, qrot_ref(hq, ld3(sens + 6 * b + 3)));
+      }
+    }
+    if (H.cfg.self_obs_v == 1) {
+      if (w.li == 0) st3(ob + o_vel, qrot_ref(hq, ld3(qvel)));
+      if (w.li == 1) st3(ob + o_vel + 3, qrot_ref(hq, ld3(qvel + 3)));
+      for (int i = w.li; i < H.nu; i += LM_LPE) ob[o_vel + 6 + i] = qvel[6 + i];
+    }
+    if (w.li == 2) {
+      const float* t = sm + C::tsk;
+      int ot = H.self_obs_dim;
+      Q4 rq; rq.w = qpos[3]; rq.x = qpos[4]; rq.y = qpos[5]; rq.z = qpos[6];
+      if (H.cfg.task == SMPLSIM_TASK_SPEED) {
+        V3 d = qrot_ref(l_heading_inv(H, rq), v3(1.f, 0.f, 0.f));
+        ob[ot] = d.x; ob[ot + 1] = d.y; ob[ot + 2] = t[0];
+      } else if (H.cfg.task == SMPLSIM_TASK_REACH) st3(ob + ot, qrot_ref(l_heading_inv(H, rq), ld3(t) - ld3(qpos)));
+      else if (H.cfg.task == SMPLSIM_TASK_GETUP) ob[ot] = t[0];
+    }
+  }
+  __syncwarp();
+  if (obs_row) l_copy_out<C>(obs_row, sm + C::obs, H.obs_dim, w);
+  __syncwarp();
+}
+
+template <class C>
+__device__ __noinline__ void l_write_aux(const float* ms, float* sm, const LLane& w, const SmplsimAux& aux, const LFwd& fo) {
+  const LHdr& H = l_hdr<C>(ms);
+  if (!w.live) return;
+  V3 root = ld3(sm + C::qpos);
+  int nb = H.nb, env = w.env;
+  for (int b = w.li; b < nb; b += LM_LPE) {
+    size_t bi = (size_t)env * nb + b;
+    if (aux.xpos) st3(aux.xpos + bi * 3, ld3(sm + C::body + C::BODYW * b + LBR_X) + root);
+    if (w.gsens) {
+      if (aux.body_linvel) st3(aux.body_linvel + bi * 3, ld3(w.gsens + 6 * b));
+      if (aux.body_angvel) st3(aux.body_angvel + bi * 3, ld3(w.gsens + 6 * b + 3));
+    }
+  }
+  if (aux.xquat) l_copy<C>(aux.xquat + (size_t)env * nb * 4, sm + C::xq, 4 * nb, w);
+  if (aux.qacc) l_copy<C>(aux.qacc + (size_t)env * H.nv, sm + C::qacc, H.nv, w);
+  if (aux.ctrl) l_copy<C>(aux.ctrl + (size_t)env * H.nu, sm + C::tau, H.nu, w);
+  if (w.li == 0) {
+    if (aux.contact_mask) aux.contact_mask[env] = fo.mask;
+    if (aux.solver_iter) aux.solver_iter[env] = fo.iters;
+    if (aux.status) aux.status[env] = (uint8_t)fo.status;
+  }
+}
+
+#ifdef SMPLSIM_EMU
+#define L_SMEM EMU_SMEM_BASE
+#else
+extern __shared__ float4 l_smem4[];
+#define L_SMEM ((float*)l_smem4)
+#endif
+
+// CTA prologue: stage the constant table, carve the env rows, claim tensor memory.  Shared memory: [table | 4 words | env rows]
+template <class C>
+__device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int img_bytes, LLane& w, const float*& ms, int n, float* gscr, float* gsens) {
+  float* smem = L_SMEM;
+  {
+    const uint4* src = (const uint4*)gimg;
+    uint4* dst = (uint4*)smem;
+    for (int i = threadIdx.x; i < img_bytes / 16; i += blockDim.x) dst[i] = src[i];
+  }
+  ms = smem;
+  unsigned* slot = (unsigned*)(smem + img_bytes / 4);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  unsigned tbase = 0u;
+#ifndef SMPLSIM_EMU
+  if (C::RECT) {
+    if (wib == 0) {
+      unsigned sa = (unsigned)__cvta_generic_to_shared(slot);
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sa) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+#else
+  if (threadIdx.x == 0) *slot = 0u;
+#endif
+  __syncthreads();
+#ifndef SMPLSIM_EMU
+  if (C::RECT) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
+  if (C::RECT) tbase = *slot;
+  const int sub = lane / LM_LPE;
+  w.lane = lane; w.li = lane % LM_LPE; w.gbase = sub * LM_LPE;
+  w.gmask = ((1u << LM_LPE) - 1u) << (sub * LM_LPE);
+  w.env = (blockIdx.x * wpb + wib) * C::EPW + sub;
+  w.live = w.env < n;
+  // tensor memory: a warp reaches the 32 lanes of its quarter (warp id mod 4); warps 4.. take the upper 256 columns
+  w.tm = tbase + ((unsigned)((wib & 3) * 32) << 16) + (unsigned)((wib >> 2) * 256);
+  w.gscr = gscr + (size_t)(w.live ? w.env : 0) * (size_t)(C::CONW * (C::NS - C::NCS));
+  w.gsens = gsens ? gsens + (size_t)(w.live ? w.env : 0) * (size_t)(6 * C::NB) : nullptr;
+  return smem + img_bytes / 4 + 4 + (size_t)(wib * C::EPW + sub) * C::total;
+}
+template <class C>
+__device__ __forceinline__ void l_teardown(const float* ms) {
+#ifndef SMPLSIM_EMU
+  if (C::RECT) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) {
+      unsigned tb = *(const unsigned*)(ms + ((const LHdr*)ms)->bytes / 4);
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+    }
+  }
+#endif
+}
+
+// stable PD, stale inertia (quirk Q1): rebuild the (M + h Kd) factors of the state of the last forward pass for the current
+// state / action.  On entry qpos / qvel / act hold the current state; qpos_fwd / qvel_fwd come from HBM.
+template <class C>
+__device__ __noinline__ void l_spd_prologue(const float* ms, float* sm, const LLane& w, const SmplsimState& sta, LSolveLane& st) {
+  const LHdr& H = l_hdr<C>(ms);
+  size_t eo = w.live ? (size_t)w.env : 0;
+  l_copy_in<C>(sm + C::qpos, sta.qpos_fwd + eo * (H.nv + 1), H.nv + 1, w);
+  l_copy_in<C>(sm + C::qvel, sta.qvel_fwd + eo * H.nv, H.nv, w);
+  __syncwarp();
+  l_sweep_out<C>(ms, sm, w, LF_FK | LF_VEL, false);
+  l_copy_in<C>(sm + C::qpos, sta.qpos + eo * (H.nv + 1), H.nv + 1, w);
+  l_copy_in<C>(sm + C::qvel, sta.qvel + eo * H.nv, H.nv, w);
+  __syncwarp();
+  l_sweep_in<C>(ms, sm, w, w.live, LI_SPD, st);
+}
+
+template <class C>
+__global__ void __launch_bounds__(256, 1) k_step5(const float* __restrict__ gimg, int img_bytes, LStepArgs a) {
+  const float* ms; LLane w;
+  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.gscr, a.gsens);
+  const LHdr& H = l_hdr<C>(ms);
+  const size_t eo = w.live ? (size_t)w.env : 0;   // lanes without a live env keep running (predicated): warp collectives stay legal
+  const bool spd = (H.cfg.control_mode == SMPLSIM_CTRL_UHC_PD);
+  LSolveLane st; st.dirty_bits = 0u; st.rc_bits = 0u; st.dispx = 0.f; st.dispy = 0.f;
+  if (w.live) for (int i = w.li; i < (H.nslot + 3) / 4; i += LM_LPE) ((int*)sm)[C::pfl + i] = 0;   // no inherited working set at launch
+  l_copy_in<C>(sm + C::act, a.action + eo * H.nu, H.nu, w);
+  if (spd && H.cfg.spd_stale && a.mode == 0) l_spd_prologue<C>(ms, sm, w, a.st, st);
+  else {
+    l_copy_in<C>(sm + C::qpos, a.st.qpos + eo * (H.nv + 1), H.nv + 1, w);
+    l_copy_in<C>(sm + C::qvel, a.st.qvel + eo * H.nv, H.nv, w);
+  }
+  l_copy_in<C>(sm + C::qacc, a.st.qacc_warm + eo * H.nv, H.nv, w);
+  if (a.mode != 0) l_copy_in<C>(sm + C::tau, a.action + eo * H.nu, H.nu, w);   // raw ctrl (act keeps a copy for the substep after an auto-reset)
+  l_task_io<C>(sm, w, a.st, false);
+  if (a.mode == 0 && w.live && w.li == 0) {
+    int* ti = (int*)(sm + C::tsk);
+    if (H.cfg.task != SMPLSIM_TASK_NONE && ti[L_TSK_CURT] >= ti[L_TSK_CHANGE]) l_reset_task<C>(H, sm, w.env);
+  }
+  __syncwarp();
+  LFwd fo; fo.mask = 0ull; fo.iters = 0; fo.status = 0;
+  l_substeps<C>(ms, sm, w, a.nsub, a.mode, &fo, a.st, true, false, st);
+  l_sweep_out<C>(ms, sm, w, LF_FK | LF_XQUAT, false);
+  if (a.mode == 0) {
+    int* ti = (int*)(sm + C::tsk);
+    if (w.live && w.li == 0) ti[L_TSK_CURT] += 1;
+    __syncwarp();
+    l_write_obs<C>(ms, sm, w, a.obs ? a.obs + eo * H.obs_dim : nullptr);
+    float dx = __shfl_sync(L_FULL, st.dispx, w.gbase), dy = __shfl_sync(L_FULL, st.dispy, w.gbase);
+    if (w.live && w.li == 0) {
+      const SmplsimEnvCfg& c = H.cfg;
+      const float* t = sm + C::tsk;
+      float rew = 0.f;
+      if (c.task == SMPLSIM_TASK_SPEED) {
+        float inv_dt = 1.0f / (H.h * (float)a.nsub), vx = dx * inv_dt, vy = dy * inv_dt, e = t[0] - vx;
+        rew = expf(-0.25f * (e * e + 0.1f * vy * vy));
+      } else if (c.task == SMPLSIM_TASK_REACH) {
+        V3 dl = ld3(t) - (ld3(sm + C::body + C::BODYW * c.reach_body + LBR_X) + ld3(sm + C::qpos));
+        rew = expf(-4.0f * dot(dl, dl));
+      } else if (c.task == SMPLSIM_TASK_GETUP) { float e = t[0] - sm[C::qpos + 2]; rew = expf(-4.0f * e * e); }
+      int term = 0, trunc = 0, pass_time = ti[L_TSK_CURT] > c.episode_length;
+      if (c.task == SMPLSIM_TASK_NONE) trunc = pass_time;
+      else if (c.task == SMPLSIM_TASK_GETUP && ti[L_TSK_RECOV] > 0) ti[L_TSK_RECOV] -= 1;
+      else { trunc = pass_time; term = (fo.mask & ~H.legal_mask) != 0ull; }
+      if (a.reward) a.reward[w.env] = rew;
+      if (a.terminated) a.terminated[w.env] = (uint8_t)term;
+      if (a.truncated) a.truncated[w.env] = (uint8_t)trunc;
+    }
+  }
+  l_write_aux<C>(ms, sm, w, a.aux, fo);
+  l_copy_out<C>(a.st.qpos + eo * (H.nv + 1), sm + C::qpos, H.nv + 1, w);
+  l_copy_out<C>(a.st.qvel + eo * H.nv, sm + C::qvel, H.nv, w);
+  l_copy_out<C>(a.st.qacc_warm + eo * H.nv, sm + C::qacc, H.nv, w);
+  if (a.mode == 0) l_task_io<C>(sm, w, a.st, true);
+  l_teardown<C>(ms);
+}
+
+template <class C>
+__global__ void __launch_bounds__(256, 1) k_reset5(const float* __restrict__ gimg, int img_bytes, LResetArgs a) {
+  const float* ms; LLane w;
+  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.gscr, a.gsens);
+  const LHdr& H = l_hdr<C>(ms);
+  if (w.live && a.mask && !a.mask[w.env]) w.live = false;
+  size_t eo = w.live ? (size_t)w.env : 0;
+  const SmplsimEnvCfg& c = H.cfg;
+  int init = a.init_mode < 0 ? c.state_init : a.init_mode;
+  LSolveLane st; st.dirty_bits = 0u; st.rc_bits = 0u; st.dispx = 0.f; st.dispy = 0.f;
+  l_task_io<C>(sm, w, a.st, false);
+  if (w.live && w.li == 0) {
+    int* ti = (int*)(sm + C::tsk);
+    if (c.task == SMPLSIM_TASK_GETUP) ti[L_TSK_RECOV] = c.recovery_steps;
+    if (!c.legacy_change_step) ti[L_TSK_CURT] = 0;
+    l_reset_task<C>(H, sm, w.env);   // sees the old cur_t when legacy_change_step (quirk Q4)
+  }
+  if (w.live) {
+    for (int i = w.li; i < (H.nslot + 3) / 4; i += LM_LPE) ((int*)sm)[C::pfl + i] = 0;
+    for (int i = w.li; i < H.nv + 1; i += LM_LPE) sm[C::qpos + i] = 0.f;
+    for (int i = w.li; i < H.nv; i += LM_LPE) { sm[C::qvel + i] = 0.f; sm[C::qacc + i] = 0.f; }
+    for (int i = w.li; i < H.nu; i += LM_LPE) { sm[C::tau + i] = 0.f; sm[C::act + i] = 0.f; }
+  }
+  __syncwarp();
+  LFwd fo; fo.mask = 0ull; fo.iters = 0; fo.status = 0;
+  if (init == SMPLSIM_INIT_MOCAP) {
+    l_copy<C>(sm + C::qpos, a.qpos0 + eo * (H.nv + 1), H.nv + 1, w);
+    l_copy<C>(sm + C::qvel, a.qvel0 + eo * H.nv, H.nv, w);
+  } else if (w.live && w.li == 0) {
+    float* q = sm + C::qpos;
+    if (init == SMPLSIM_INIT_DEFAULT) { q[2] = 0.94f; q[3] = q[4] = q[5] = q[6] = 0.5f; }
+    else { q[2] = 0.3f; q[3] = 1.0f; }
+  }
+  __syncwarp();
+  if (init == SMPLSIM_INIT_FALL) {
+    const bool spd_st = (c.control_mode == SMPLSIM_CTRL_UHC_PD && c.spd_stale);
+    if (spd_st) l_sweep_out<C>(ms, sm, w, LF_FK | LF_VEL, false);   // mj_forward: inertia / bias of the initial state
+    int ngrp = (H.nu + 3) / 4;
+    for (int k3 = 0; k3 < 3; k3++) {
+      int* ti = (int*)(sm + C::tsk);
+      uint32_t base = w.live ? (uint32_t)ti[L_TSK_RNG] : 0u;
+      if (w.live) {
+        for (int gidx = w.li; gidx < ngrp; gidx += LM_LPE) {
+          uint32_t r[4];
+          philox4x32(base + (uint32_t)gidx, (uint32_t)w.env, 0u, 0u, (uint32_t)c.seed, (uint32_t)(c.seed >> 32), r);
+          for (int j = 0; j < 4 && 4 * gidx + j < H.nu; j++) sm[C::act + 4 * gidx + j] = u01(r[j]) - 0.5f;
+        }
+      }
+      __syncwarp();
+      if (w.live && w.li == 0) ti[L_TSK_RNG] = (int)(base + (uint32_t)ngrp);
+      __syncwarp();
+      if (spd_st) l_sweep_in<C>(ms, sm, w, w.live, LI_SPD, st);   // factors of the last forward pass, PD error of the current state and the new action
+      l_substeps<C>(ms, sm, w, c.nsubsteps, 0, &fo, a.st, false, false, st);
+    }
+  }
+  // reset_sim(): mj_forward at the reset state
+  {
+    LFkOut fk = l_sweep_out<C>(ms, sm, w, LF_FK | LF_VEL | LF_COLLIDE | LF_SENS, false);
+    fo.mask = fk.mask;
+  }
+  if (w.live && w.li == 0) ((int*)(sm + C::tsk))[L_TSK_CURT] = 0;
+  __syncwarp();
+  l_sweep_out<C>(ms, sm, w, LF_FK | LF_XQUAT, false);
+  l_write_obs<C>(ms, sm, w, a.obs ? a.obs + eo * H.obs_dim : nullptr);
+  l_write_aux<C>(ms, sm, w, a.aux, fo);
+  l_copy_out<C>(a.st.qpos + eo * (H.nv + 1), sm + C::qpos, H.nv + 1, w);
+  l_copy_out<C>(a.st.qvel + eo * H.nv, sm + C::qvel, H.nv, w);
+  l_copy_out<C>(a.st.qpos_fwd + eo * (H.nv + 1), sm + C::qpos, H.nv + 1, w);
+  l_copy_out<C>(a.st.qvel_fwd + eo * H.nv, sm + C::qvel, H.nv, w);
+  l_copy_out<C>(a.st.qacc_warm + eo * H.nv, sm + C::qacc, H.nv, w);
+  l_task_io<C>(sm, w, a.st, true);
+  l_teardown<C>(ms);
+}
+
+// mujoco.mj_kinematics (humanoid_env.py:389) / poselib global_transformation on caller-supplied qpos rows
+template <class C>
+__global__ void __launch_bounds__(256, 1) k_kin5(const float* __restrict__ gimg, int img_bytes, LKinArgs a) {
+  const float* ms; LLane w;
+  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, nullptr, nullptr);
+  const LHdr& H = l_hdr<C>(ms);
+  size_t eo = w.live ? (size_t)w.env : 0;
+  l_copy<C>(sm + C::qpos, a.qpos + eo * (H.nv + 1), H.nv + 1, w);
+  __syncwarp();
+  l_sweep_out<C>(ms, sm, w, LF_FK | LF_XQUAT, false);
+  if (w.live) {
+    V3 root = ld3(sm + C::qpos);
+    for (int b = w.li; b < H.nb; b += LM_LPE) st3(a.xpos + (eo * H.nb + b) * 3, ld3(sm + C::body + C::BODYW * b + LBR_X) + root);
+    l_copy<C>(a.xquat + eo * H.nb * 4, sm + C::xq, 4 * H.nb, w);
+  }
+  l_teardown<C>(ms);
+}

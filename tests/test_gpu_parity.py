@@ -1,4 +1,6 @@
-"""GPU parity tests: CUDA path (through the C ABI) vs the fp64 oracle / reference-generated goldens.
+"""Parity tests: the kernels (through the C ABI) vs the fp64 oracle / reference-generated goldens.
+Every test runs on the GPU (`-m gpu`: libsmplsim_b200.so on cuda:0 -- the parity claim) and, where the size allows, once more
+on the host SIMT emulator (tests/emu: the same kernel sources compiled for the CPU; part of the `-m "not gpu"` suite).
 
 Tolerances: north_star asks for 1e-4 relative (fp32) on qpos/qvel after one mj_step and bit-exact
 floor-contact flags; relerr(a,b) = max|a-b| / max(1, max|b|).
@@ -13,20 +15,11 @@ from conftest import GOLDEN  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 from util_states import airborne_states, make_models, relerr, rollout_states  # noqa: E402
 
-pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-def _batch(cfg, n, seed=0):
-    from smplsim_b200.batched import HumanoidBatchB200
-    return HumanoidBatchB200(cfg, num_envs=n, device="cuda:0", seed=seed)
-
-
-def _t(x, dtype=torch.float32):
-    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype, device="cuda:0")
-
-
-def test_extension_loaded_and_symbols():
+@pytest.mark.gpu_only
+def test_extension_loaded_and_symbols(backend):
     from smplsim_b200 import _lib
     L = _lib.lib()
     assert L.smplsim_version() >= 100
@@ -35,13 +28,13 @@ def test_extension_loaded_and_symbols():
 
 
 @pytest.mark.parametrize("robot", ["smpl_humanoid", "smplx_humanoid"])
-def test_kinematics_matches_oracle(robot):
+def test_kinematics_matches_oracle(backend, robot):
     cfg, om = make_models(robot=robot)
     m = om.model
     q, _ = airborne_states(m, 64, seed=1)
     q[:, 0:2] *= 10
-    env = _batch(cfg, 1)
-    xpos, xquat = env.kinematics(_t(q))
+    env = backend.batch(cfg, 1)
+    xpos, xquat = env.kinematics(backend.t(q))
     e = orc.OracleEnv(om)
     for i in range(q.shape[0]):
         e.qpos[:] = q[i]; e.kinematics()
@@ -51,14 +44,14 @@ def test_kinematics_matches_oracle(robot):
 
 
 @pytest.mark.parametrize("name,robot", [("smpl", "smpl_humanoid"), ("smplx", "smplx_humanoid")])
-def test_self_obs_matches_reference_golden(name, robot):
+def test_self_obs_matches_reference_golden(backend, name, robot):
     g = np.load(os.path.join(GOLDEN, f"obs_{name}.npz"))
     for upright, rh in ((False, True), (False, False), (True, True)):
         cfg, om = make_models(robot=robot, **{"root_height_obs": rh, "robot.has_upright_start": upright})
-        env = _batch(cfg, 1)
+        env = backend.batch(cfg, 1)
         tag = f"u{int(upright)}h{int(rh)}"
-        o1 = env.self_obs(1, _t(g["xpos"]), _t(g["xquat"]), qvel=_t(g["qvel"])).cpu().numpy()
-        o2 = env.self_obs(2, _t(g["xpos"]), _t(g["xquat"]), linvel=_t(g["linvel"]), angvel=_t(g["angvel"])).cpu().numpy()
+        o1 = env.self_obs(1, backend.t(g["xpos"]), backend.t(g["xquat"]), qvel=backend.t(g["qvel"])).cpu().numpy()
+        o2 = env.self_obs(2, backend.t(g["xpos"]), backend.t(g["xquat"]), linvel=backend.t(g["linvel"]), angvel=backend.t(g["angvel"])).cpu().numpy()
         # xpos is absolute (|x| up to 20 m) in fp32 -> 2e-6 absolute resolution on local positions
         assert np.abs(o1 - g["v1_" + tag]).max() < 2e-5
         assert np.abs(o2 - g["v2_" + tag]).max() < 2e-5
@@ -72,7 +65,7 @@ def _oracle_one_step(om, q, v, w, ctrl):
 
 
 @pytest.mark.parametrize("robot", ["smpl_humanoid", "smplx_humanoid"])
-def test_mj_step_airborne(robot):
+def test_mj_step_airborne(backend, robot):
     """No contact: qacc = M^-1 (tau - c) through ABA vs the oracle's CRB + L'DL."""
     cfg, om = make_models(robot=robot, control_mode="torque")
     m = om.model
@@ -80,9 +73,9 @@ def test_mj_step_airborne(robot):
     q, v = airborne_states(m, n, seed=3)
     rng = np.random.default_rng(5)
     ctrl = rng.uniform(-50, 50, (n, m.nu))
-    env = _batch(cfg, n)
-    env.set_state(_t(q), _t(v))
-    env.mj_step(_t(ctrl), 1)
+    env = backend.batch(cfg, n)
+    env.set_state(backend.t(q), backend.t(v))
+    env.mj_step(backend.t(ctrl), 1)
     gq, gv, ga = env.qpos.cpu().numpy(), env.qvel.cpu().numpy(), env.qacc.cpu().numpy()
     for i in range(n):
         e = _oracle_one_step(om, q[i], v[i], np.zeros(m.nv), ctrl[i])
@@ -91,15 +84,15 @@ def test_mj_step_airborne(robot):
         assert relerr(gq[i], e.qpos) < TOL, ("qpos", i, relerr(gq[i], e.qpos))
 
 
-def test_free_fall_closed_form():
+def test_free_fall_closed_form(backend):
     """K-3: semi-implicit Euler free fall, v_z = -g n h, z = z0 - g h^2 n(n+1)/2; joints stay at rest."""
     cfg, om = make_models(control_mode="torque")
     m = om.model
-    env = _batch(cfg, 4)
+    env = backend.batch(cfg, 4)
     q = np.zeros((4, m.nq)); q[:, 2] = 5.0; q[:, 3] = 1.0
-    env.set_state(_t(q), _t(np.zeros((4, m.nv))))
+    env.set_state(backend.t(q), backend.t(np.zeros((4, m.nv))))
     n, h = 30, m.timestep
-    env.mj_step(_t(np.zeros((4, m.nu))), n)
+    env.mj_step(backend.t(np.zeros((4, m.nu))), n)
     gq, gv = env.qpos.cpu().numpy(), env.qvel.cpu().numpy()
     assert np.abs(gv[:, 2] + 9.81 * n * h).max() < 1e-5
     assert np.abs(gq[:, 2] - (5.0 - 9.81 * h * h * n * (n + 1) / 2)).max() < 1e-5
@@ -107,7 +100,7 @@ def test_free_fall_closed_form():
 
 
 @pytest.mark.parametrize("mode", ["torque", "uhc_pd"])
-def test_mj_step_contact_states(mode):
+def test_mj_step_contact_states(backend, mode):
     """One substep from standing / stumbling / fallen states: qpos, qvel to 1e-4, contact geom flags bit-exact
     (outside a |dist - margin| < 1e-5 guard band), through mj_step with the oracle's own torque."""
     cfg, om = make_models(control_mode=mode)
@@ -116,10 +109,10 @@ def test_mj_step_contact_states(mode):
     q, v, w = rollout_states(make_models(control_mode="uhc_pd")[1], n, seed=11)   # states from stable-PD rollouts
     rng = np.random.default_rng(2)
     ctrl = rng.uniform(-80, 80, (n, m.nu))
-    env = _batch(cfg, n)
-    env.set_state(_t(q), _t(v))
-    env.qacc_warm.copy_(_t(w))
-    env.mj_step(_t(ctrl), 1)
+    env = backend.batch(cfg, n)
+    env.set_state(backend.t(q), backend.t(v))
+    env.qacc_warm.copy_(backend.t(w))
+    env.mj_step(backend.t(ctrl), 1)
     gq, gv, ga = env.qpos.cpu().numpy(), env.qvel.cpu().numpy(), env.qacc.cpu().numpy()
     gmask = env.contact_mask.cpu().numpy().astype(np.uint64)
     it = env.solver_iter.cpu().numpy()
@@ -169,7 +162,7 @@ def _near_margin(om, q, diffmask):
 
 
 @pytest.mark.parametrize("mode", ["uhc_pd", "pd", "torque"])
-def test_controller_torque_matches_oracle(mode):
+def test_controller_torque_matches_oracle(backend, mode):
     """compute_torque (incl. the stale-M stable PD, quirk Q1) as applied in the first substep of env.step."""
     cfg, om = make_models(env="speed", control_mode=mode)
     m = om.model
@@ -180,12 +173,12 @@ def test_controller_torque_matches_oracle(mode):
     qs = q.copy(); qs[:, 7:] += rng.normal(size=(n, m.nu)) * 0.003      # last-forward state differs slightly
     from smplsim_b200.cfg import make_cfg
     cfg1 = make_cfg(env="speed", overrides={"env.control_mode": mode, "env.control_frequency_inv": 1})
-    env = _batch(cfg1, n)
-    env.set_state(_t(q), _t(v))
-    env.qpos_fwd.copy_(_t(qs)); env.qvel_fwd.copy_(_t(v * 0.9))
-    env.qacc_warm.copy_(_t(w))
+    env = backend.batch(cfg1, n)
+    env.set_state(backend.t(q), backend.t(v))
+    env.qpos_fwd.copy_(backend.t(qs)); env.qvel_fwd.copy_(backend.t(v * 0.9))
+    env.qacc_warm.copy_(backend.t(w))
     env.task_change_step.fill_(10000)
-    env.step(_t(act))
+    env.step(backend.t(act))
     gt = env.ctrl.cpu().numpy()
     st = env.status.cpu().numpy()
     assert (st != 0).sum() <= 2
@@ -203,13 +196,13 @@ def test_controller_torque_matches_oracle(mode):
 
 
 @pytest.mark.parametrize("task,obs_v", [("speed", 1), ("reach", 2), ("getup", 1)])
-def test_env_step_matches_oracle(task, obs_v):
+def test_env_step_matches_oracle(backend, task, obs_v):
     """reset + a few env steps (15 substeps each): obs / reward / flags / task sampling vs the oracle."""
     ov = {"self_obs_v": obs_v, "robot.create_vel_sensors": True}
     cfg, om = make_models(env=task, seed=123, **ov)
     m = om.model
     n = 16
-    env = _batch(cfg, n, seed=123)
+    env = backend.batch(cfg, n, seed=123)
     obs0 = env.reset().cpu().numpy().copy()
     oes = [orc.OracleEnv(om, env_id=i) for i in range(n)]
     rng = np.random.default_rng(9)
@@ -222,7 +215,7 @@ def test_env_step_matches_oracle(task, obs_v):
     nsteps = 3
     for t in range(nsteps):
         act = np.clip(rng.normal(size=(n, m.nu)) * 0.1, -1, 1)
-        obs, rew, term, trunc = [x.cpu().numpy() for x in env.step(_t(act))]
+        obs, rew, term, trunc = [x.cpu().numpy() for x in env.step(backend.t(act))]
         for i, e in enumerate(oes):
             o, r, te, tr = e.step(act[i])
             tol = 5e-4 * (t + 1) * (10 if task == "getup" else 1)
@@ -231,17 +224,18 @@ def test_env_step_matches_oracle(task, obs_v):
             assert bool(term[i]) == te and bool(trunc[i]) == tr
 
 
-def test_many_envs_identical_and_deterministic():
+@pytest.mark.gpu_only
+def test_many_envs_identical_and_deterministic(backend):
     """4096 envs (BASELINE config 2 size): identical inputs give bit-identical outputs in every env and across runs."""
     cfg, om = make_models(env="speed")
     m = om.model
     n = 4096
     outs = []
     for rep in range(2):
-        env = _batch(cfg, n, seed=7)
+        env = backend.batch(cfg, n, seed=7)
         env.reset()
         env.task_target[:, 0] = 1.5
-        a = torch.zeros(n, m.nu, device="cuda:0"); a[:, 3] = 0.2
+        a = torch.zeros(n, m.nu, device=backend.device); a[:, 3] = 0.2
         for _ in range(4):
             env.step(a)
         outs.append((env.qpos.clone(), env.obs_buf.clone(), env.rew_buf.clone()))
@@ -251,31 +245,31 @@ def test_many_envs_identical_and_deterministic():
     assert torch.isfinite(o).all()
 
 
-def test_fall_init_and_recovery_counter():
+def test_fall_init_and_recovery_counter(backend):
     cfg, om = make_models(env="getup", seed=5)
     n = 8
-    env = _batch(cfg, n, seed=5)
+    env = backend.batch(cfg, n, seed=5)
     env.reset()
     assert (env.recovery.cpu().numpy() == 60).all()
     q = env.qpos.cpu().numpy()
     assert (q[:, 2] < 0.35).all() and (q[:, 2] > 0.02).all()
     e = orc.OracleEnv(om, env_id=3); e.reset()
     assert relerr(q[3], e.qpos) < 5e-3
-    a = torch.zeros(n, om.model.nu, device="cuda:0")
+    a = torch.zeros(n, om.model.nu, device=backend.device)
     _, _, term, trunc = env.step(a)
     assert not term.any() and not trunc.any() and (env.recovery.cpu().numpy() == 59).all()
 
 
-def test_masked_reset_only_touches_flagged_envs():
+def test_masked_reset_only_touches_flagged_envs(backend):
     cfg, om = make_models(env="speed")
     n = 8
-    env = _batch(cfg, n)
+    env = backend.batch(cfg, n)
     env.reset()
-    a = torch.zeros(n, om.model.nu, device="cuda:0")
+    a = torch.zeros(n, om.model.nu, device=backend.device)
     for _ in range(3):
         env.step(a)
     before = env.qpos.clone()
-    mask = torch.zeros(n, dtype=torch.uint8, device="cuda:0"); mask[2] = 1; mask[5] = 1
+    mask = torch.zeros(n, dtype=torch.uint8, device=backend.device); mask[2] = 1; mask[5] = 1
     env.reset(mask)
     after = env.qpos
     keep = [0, 1, 3, 4, 6, 7]
@@ -283,11 +277,10 @@ def test_masked_reset_only_touches_flagged_envs():
     assert abs(after[2, 2].item() - 0.94) < 1e-6 and env.progress_buf[2].item() == 0 and env.progress_buf[0].item() == 3
 
 
-def test_joint_limit_rows_match_oracle():
+def test_joint_limit_rows_match_oracle(backend):
     """Tightened hinge ranges (what robot.has_jt_limit does in the reference, smpllib/smpl_local_robot.py:176-245) make
     limit rows routinely active; one substep vs the oracle, with and without floor contact."""
     from smplsim_b200.abi import env_cfg_from, model_from_cfg
-    from smplsim_b200.batched import HumanoidBatchB200
     from smplsim_b200.cfg import make_cfg
     cfg = make_cfg(env="speed", overrides={"env.control_mode": "torque"})
     m = model_from_cfg(cfg)
@@ -301,9 +294,9 @@ def test_joint_limit_rows_match_oracle():
     n = q.shape[0]
     rng = np.random.default_rng(8)
     ctrl = rng.uniform(-60, 60, (n, m.nu))
-    env = HumanoidBatchB200(cfg, num_envs=n, model=m)
-    env.set_state(_t(q), _t(v)); env.qacc_warm.copy_(_t(w))
-    env.mj_step(_t(ctrl), 1)
+    env = backend.batch(cfg, n, model=m)
+    env.set_state(backend.t(q), backend.t(v)); env.qacc_warm.copy_(backend.t(w))
+    env.mj_step(backend.t(ctrl), 1)
     gq, gv = env.qpos.cpu().numpy(), env.qvel.cpu().numpy()
     nlim_total = 0
     for i in range(n):
@@ -320,14 +313,14 @@ def test_joint_limit_rows_match_oracle():
     assert nlim_total > n
 
 
-def test_env_step_explicit_pd_single_substep():
+def test_env_step_explicit_pd_single_substep(backend):
     """explicit-PD controller through env.step with one substep per step (with kp=800, kd=80 at h=1/450 the explicit
     controller is numerically unstable over 15 substeps -- the reason the reference defaults to stable PD -- so longer
     trajectories are chaotic and cannot be compared)."""
     cfg, om = make_models(env="speed", seed=4, control_mode="pd", control_frequency_inv=1)
     m = om.model
     n = 8
-    env = _batch(cfg, n, seed=4)
+    env = backend.batch(cfg, n, seed=4)
     env.reset()
     oes = [orc.OracleEnv(om, env_id=i) for i in range(n)]
     for e in oes:
@@ -335,21 +328,21 @@ def test_env_step_explicit_pd_single_substep():
     rng = np.random.default_rng(3)
     for t in range(2):
         act = np.clip(rng.normal(size=(n, m.nu)) * 0.05, -1, 1)
-        obs, rew, term, trunc = [x.cpu().numpy() for x in env.step(_t(act))]
+        obs, rew, term, trunc = [x.cpu().numpy() for x in env.step(backend.t(act))]
         for i, e in enumerate(oes):
             o, r, te, tr = e.step(act[i])
             # per-step error amplification of the explicit controller is ~ kd*h/I >> 1 on the light links
             assert np.abs(obs[i] - o).max() < 2e-3 * 20 ** t, (t, i, np.abs(obs[i] - o).max())
 
 
-def test_spd_fresh_mode_runs_and_differs_slightly():
+def test_spd_fresh_mode_runs_and_differs_slightly(backend):
     """cfg.env.spd_inertia='fresh' (quirk Q1 switched off): finite, and close to -- but not identical with -- the stale default."""
     outs = {}
     for spd in ("stale", "fresh"):
         cfg, om = make_models(env="speed", seed=4, spd_inertia=spd)
-        env = _batch(cfg, 8, seed=4)
+        env = backend.batch(cfg, 8, seed=4)
         env.reset()
-        a = torch.zeros(8, om.model.nu, device="cuda:0"); a[:, 10] = 0.3
+        a = torch.zeros(8, om.model.nu, device=backend.device); a[:, 10] = 0.3
         for _ in range(2):
             env.step(a)
         outs[spd] = env.qpos.cpu().numpy().copy()
@@ -358,7 +351,7 @@ def test_spd_fresh_mode_runs_and_differs_slightly():
     assert 0 < d < 5e-2, d
 
 
-def test_regression_line_search_noise_floor():
+def test_regression_line_search_noise_floor(backend):
     """Captured case (round 1): from the Default reset pose with this action, substep 7's active-set iterate was already
     optimal to fp32 rounding but one row sat at r ~ 0, so the set comparison asked for another line search; its directional
     derivative (-3e-6, pure cancellation noise against g1 = 0.076) and curvature (-3e-6) sent the step to 2^24 and the env
@@ -366,14 +359,14 @@ def test_regression_line_search_noise_floor():
     caps the extrapolation; the step must match the oracle replay."""
     d = np.load(os.path.join(GOLDEN, "regress_default_step_case1.npz"))
     cfg, om = make_models(env="speed")
-    env = _batch(cfg, 64, seed=0)
+    env = backend.batch(cfg, 64, seed=0)
     env.reset()
     env.task_change_step.fill_(10 ** 6)   # the speed target only enters obs / reward
     e = orc.OracleEnv(om, env_id=0)
     e.reset()
     assert np.abs(env.qpos[0].cpu().numpy() - d["qpos"]).max() < 1e-6
     act = np.repeat(d["action"][None], 64, 0)
-    env.step(_t(act))
+    env.step(backend.t(act))
     e.step(d["action"].astype(np.float64))
     qp, qv = env.qpos.cpu().numpy(), env.qvel.cpu().numpy()
     assert np.array_equal(qp, np.repeat(qp[:1], 64, 0))
@@ -382,14 +375,14 @@ def test_regression_line_search_noise_floor():
 
 
 @pytest.mark.parametrize("case", ["nan_qpos", "huge_qvel", "bad_qacc"])
-def test_bad_state_autoreset_matches_mj_step_semantics(case):
+def test_bad_state_autoreset_matches_mj_step_semantics(backend, case):
     """mj_checkPos / mj_checkVel / mj_checkAcc + mj_resetData: a NaN or |x| > 1e10 never reaches the caller --
     the env's data is reset to qpos0 / zero velocity inside the substep, the warning bit is reported in aux.status, and the
     rest of the env step proceeds from there exactly like the oracle."""
     cfg, om = make_models(env="speed")
     m = om.model
     n = 8
-    env = _batch(cfg, n, seed=0)
+    env = backend.batch(cfg, n, seed=0)
     env.reset()
     e = orc.OracleEnv(om, env_id=3)
     e.reset()
@@ -403,7 +396,7 @@ def test_bad_state_autoreset_matches_mj_step_semantics(case):
     env.set_state(qp, qv)
     e.forward()
     act = np.zeros((n, m.nu)); act[:] = 0.05
-    obs, rew, term, trunc = env.step(_t(act))
+    obs, rew, term, trunc = env.step(backend.t(act))
     st = env.status.cpu().numpy()
     e.warn = 0
     o, r, te, tr = e.step(act[3])
@@ -416,12 +409,12 @@ def test_bad_state_autoreset_matches_mj_step_semantics(case):
         assert np.array_equal(env.qpos[i].cpu().numpy(), ref)
 
 
-def test_env_step_simple_pid_matches_oracle():
+def test_env_step_simple_pid_matches_oracle(backend):
     """control_mode simple_pid: the stateful SimplePID (integral / last error carried across substeps, steps and resets)."""
     cfg, om = make_models(env="speed", control_mode="simple_pid", seed=5)
     m = om.model
     n = 8
-    env = _batch(cfg, n, seed=5)
+    env = backend.batch(cfg, n, seed=5)
     env.reset()
     oes = [orc.OracleEnv(om, env_id=i) for i in range(n)]
     for e in oes:
@@ -429,7 +422,7 @@ def test_env_step_simple_pid_matches_oracle():
     rng = np.random.default_rng(2)
     for t in range(3):
         act = np.clip(rng.normal(size=(n, m.nu)) * 0.1, -1, 1)
-        obs, rew, term, trunc = [x.cpu().numpy() for x in env.step(_t(act))]
+        obs, rew, term, trunc = [x.cpu().numpy() for x in env.step(backend.t(act))]
         gi, gl = env.pid_integral.cpu().numpy(), env.pid_last_error.cpu().numpy()
         for i, e in enumerate(oes):
             o, r, te, tr = e.step(act[i])
