@@ -30,7 +30,10 @@
 #define L_FULL 0xffffffffu
 #define L_SOLVER_MAXITER 16
 #define L_LS_MAXITER 24
-#define L_LS_NOISE 1e-4f     // line search: directional derivative below this fraction of its two cancelling parts = converged
+#ifndef L_LS_NOISE
+#define L_LS_NOISE 1e-4f
+#endif
+//   L_LS_NOISE:     // line search: directional derivative below this fraction of its two cancelling parts = converged
 #define L_LS_MAXSTEP 16.f    // line search: never extrapolate further than this multiple of the Newton step
 #define L_MAXVAL 1e10f       // mjMAXVAL (mj_checkPos / Vel / Acc)
 // aux.status bits beyond mj_warning's 1 BADQPOS | 2 BADQVEL | 4 BADQACC
@@ -108,6 +111,9 @@ __device__ __forceinline__ float l_gsum(float v) {
 }
 __device__ __forceinline__ bool l_gall(bool p, const LLane& w) { return (__ballot_sync(L_FULL, p) & w.gmask) == w.gmask; }
 __device__ __forceinline__ bool l_gany(bool p, const LLane& w) { return (__ballot_sync(L_FULL, p) & w.gmask) != 0u; }
+
+// joint-diagonal reciprocal: MUFU.RCP + one multiply (1 ulp) instead of the IEEE division sequence with its slow path
+__device__ __forceinline__ float l_rcp(float x) { return __fdividef(1.0f, x); }
 
 __device__ __forceinline__ void l_sincos(float x, float* s, float* c) {
   float k = rintf(x * 0.63661977236758134f);
@@ -326,6 +332,45 @@ __device__ __forceinline__ int l_gscan(int v, const LLane& w, int* total) {
   return inc - v;
 }
 
+// root body of the outward sweep (free joint, lane 0 of the group at step 0): stable-PD acceleration of the six root dofs from
+// the stored factors, then pose / velocity / bias acceleration of the state in qpos, qvel
+template <class C>
+__device__ __noinline__ void l_root_out(const float* ms, float* sm, int flags, Q4& cq, V3& cx, S6& cv, S6& cab, S6& casp) {
+  const LHdr& H = l_hdr<C>(ms);
+  float* br = sm + C::body;
+  float* qpos = sm + C::qpos;
+  const float* qvel = sm + C::qvel;
+  if (flags & LF_GOUT) {      // old rotation columns (FK rows of the last forward pass)
+    const float* rt = sm + C::root;
+    S6 a = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
+                     : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
+      float qdd = rt[36 + k] - dot6(l_arr6(rt + 6 * k), a);
+      a = a + qdd * S;
+    }
+    casp = a;
+  }
+  if (flags & LF_FK) {
+    Q4 qc;
+    qc.w = qpos[3]; qc.x = qpos[4]; qc.y = qpos[5]; qc.z = qpos[6];
+    qc = qnormalize(qc);
+    qpos[3] = qc.w; qpos[4] = qc.x; qpos[5] = qc.y; qpos[6] = qc.z;
+    float R[9];
+    q2mat(qc, R);
+    V3 c0 = v3(R[0], R[3], R[6]), c1 = v3(R[1], R[4], R[7]), c2 = v3(R[2], R[5], R[8]);
+    st3(br + LBR_AX, c0); st3(br + LBR_AX + 3, c1); st3(br + LBR_AX + 6, c2);
+    st3(br + LBR_X, v3(0.f, 0.f, 0.f));
+    cq = qc; cx = v3(0.f, 0.f, 0.f);
+    if (flags & LF_VEL) {
+      V3 vl = ld3(qvel), wv = qvel[3] * c0 + qvel[4] * c1 + qvel[5] * c2;
+      cv = s6(wv, vl);
+      cab = s6(v3(0.f, 0.f, 0.f), v3(-H.grav[0], -H.grav[1], -H.grav[2]) + cross(vl, wv));
+    }
+  }
+}
+
 template <class C>
 __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLane& w, int flags, bool ztau) {
   const LHdr& H = l_hdr<C>(ms);
@@ -343,7 +388,7 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
     const int b = H.sched[t][w.li];
     const bool actv = w.live && b >= 0;
     float K[18], kc[3];
-    if ((flags & LF_GOUT) && !H.step_root[t]) l_rec_ld_Kc<C>(w, sm, t, b, K, kc);
+    if ((flags & LF_GOUT) && t > 0) l_rec_ld_Kc<C>(w, sm, t, b, K, kc);
     S6 pbv = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
     float* br = sm + C::body + C::BODYW * (actv ? b : 0);
     int alloc = 0, nlr = 0, g = 0;   // contact entries / limit rows this lane wants; its geom
@@ -356,39 +401,9 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
     if (actv) {
       const LBody& lb = MB[b];
       Q4 qc; V3 x; S6 v, ab;
-      if (b == 0) {
-        // ---------------- root: free joint
-        float* qpos = sm + C::qpos;
-        const float* qvel = sm + C::qvel;
-        if (flags & LF_GOUT) {      // acceleration of the 6 root dofs from the stored factors (old rotation columns)
-          const float* rt = sm + C::root;
-          S6 a = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
-#pragma unroll
-          for (int k = 0; k < 6; k++) {
-            S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
-                           : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
-            float qdd = rt[36 + k] - dot6(l_arr6(rt + 6 * k), a);
-            a = a + qdd * S;
-          }
-          casp = a;
-        }
+      if (t == 0) {   // the root body (free joint): out of line, once per sweep
+        l_root_out<C>(ms, sm, flags, cq, cx, cv, cab, casp);
         qc = cq; x = cx; v = cv; ab = cab;
-        if (flags & LF_FK) {
-          qc.w = qpos[3]; qc.x = qpos[4]; qc.y = qpos[5]; qc.z = qpos[6];
-          qc = qnormalize(qc);
-          qpos[3] = qc.w; qpos[4] = qc.x; qpos[5] = qc.y; qpos[6] = qc.z;
-          x = v3(0.f, 0.f, 0.f);
-          float R[9];
-          q2mat(qc, R);
-          V3 c0 = v3(R[0], R[3], R[6]), c1 = v3(R[1], R[4], R[7]), c2 = v3(R[2], R[5], R[8]);
-          st3(br + LBR_AX, c0); st3(br + LBR_AX + 3, c1); st3(br + LBR_AX + 6, c2);
-          st3(br + LBR_X, x);
-          if (flags & LF_VEL) {
-            V3 vl = ld3(qvel), wv = qvel[3] * c0 + qvel[4] * c1 + qvel[5] * c2;
-            v = s6(wv, vl);
-            ab = s6(v3(0.f, 0.f, 0.f), v3(-H.grav[0], -H.grav[1], -H.grav[2]) + cross(vl, wv));
-          }
-        }
       } else {
         // ---------------- hinge body
         const int d0 = lb.dofadr;
@@ -606,6 +621,55 @@ struct LSolveLane {       // lane-private sweep bookkeeping of one substep
   float dispx, dispy;     // root displacement of this substep (lane of the root body)
 };
 
+// root body of the inward sweep: (semi-implicit Euler of the free joint, then) elimination of its six dofs; the factors
+// K (6 x 6) and c (6) stay in shared memory
+template <class C>
+__device__ __noinline__ void l_root_in(const float* ms, float* sm, int flags, float* A, S6& p, LSolveLane& st) {
+  const LHdr& H = l_hdr<C>(ms);
+  float* br = sm + C::body;
+    float* rt = sm + C::root;
+    if (flags & LI_INTEGRATE) {
+      float* qpos = sm + C::qpos; float* qvel = sm + C::qvel; const float* qacc = sm + C::qacc;
+      float h = H.h;
+#pragma unroll
+      for (int d = 0; d < 6; d++) {
+        float v = fmaf(h, qacc[d], qvel[d]);
+        qvel[d] = v;
+        if (d < 3) { float dd = h * v; qpos[d] += dd; if (d == 0) st.dispx += dd; if (d == 1) st.dispy += dd; }
+      }
+      V3 wv = ld3(qvel + 3);
+      float n = sqrtf(dot(wv, wv)), ang = n * h;
+      Q4 q; q.w = qpos[3]; q.x = qpos[4]; q.y = qpos[5]; q.z = qpos[6];
+      if (ang > 0.f) {
+        float sn, cs;
+        l_sincos(0.5f * ang, &sn, &cs);
+        float s = sn / n;
+        Q4 dq; dq.w = cs; dq.x = wv.x * s; dq.y = wv.y * s; dq.z = wv.z * s;
+        q = qmul(q, dq);
+      }
+      q = qnormalize(q);
+      qpos[3] = q.w; qpos[4] = q.x; qpos[5] = q.y; qpos[6] = q.z;
+    }
+#pragma unroll
+    for (int k = 5; k >= 0; k--) {
+      S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
+                     : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
+      float s[6], Uv[6];
+      l_s6arr(S, s);
+      sym_mul(A, s, Uv);
+      float D = H.rarm[k];
+#pragma unroll
+      for (int j = 0; j < 6; j++) D = fmaf(s[j], Uv[j], D);
+      float di = l_rcp(D);
+      float uu = -dot6(S, p);
+      sym_rank1(A, Uv, di);
+      p = p + (uu * di) * l_arr6(Uv);
+#pragma unroll
+      for (int j = 0; j < 6; j++) rt[6 * k + j] = Uv[j] * di;
+      rt[36 + k] = uu * di;
+    }
+}
+
 template <class C>
 __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane& w, bool run, int flags, LSolveLane& st) {
   const LHdr& H = l_hdr<C>(ms);
@@ -673,49 +737,8 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
           for (int kk = 0; kk < 3; kk++) if (kk == k) { lD[kk] = le[LLE_D]; lT[kk] = le[LLE_SG] * le[LLE_D] * le[LLE_AREF]; }
         }
       }
-      if (b == 0) {
-        // ---------------- root: six free-joint dofs, factors kept in shared memory
-        float* rt = sm + C::root;
-        if (flags & LI_INTEGRATE) {
-          float* qpos = sm + C::qpos; float* qvel = sm + C::qvel; const float* qacc = sm + C::qacc;
-          float h = H.h;
-#pragma unroll
-          for (int d = 0; d < 6; d++) {
-            float v = fmaf(h, qacc[d], qvel[d]);
-            qvel[d] = v;
-            if (d < 3) { float dd = h * v; qpos[d] += dd; if (d == 0) st.dispx += dd; if (d == 1) st.dispy += dd; }
-          }
-          V3 wv = ld3(qvel + 3);
-          float n = sqrtf(dot(wv, wv)), ang = n * h;
-          Q4 q; q.w = qpos[3]; q.x = qpos[4]; q.y = qpos[5]; q.z = qpos[6];
-          if (ang > 0.f) {
-            float sn, cs;
-            l_sincos(0.5f * ang, &sn, &cs);
-            float s = sn / n;
-            Q4 dq; dq.w = cs; dq.x = wv.x * s; dq.y = wv.y * s; dq.z = wv.z * s;
-            q = qmul(q, dq);
-          }
-          q = qnormalize(q);
-          qpos[3] = q.w; qpos[4] = q.x; qpos[5] = q.y; qpos[6] = q.z;
-        }
-#pragma unroll
-        for (int k = 5; k >= 0; k--) {
-          S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
-                         : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
-          float s[6], Uv[6];
-          l_s6arr(S, s);
-          sym_mul(A, s, Uv);
-          float D = H.rarm[k];
-#pragma unroll
-          for (int j = 0; j < 6; j++) D = fmaf(s[j], Uv[j], D);
-          float di = 1.0f / D;
-          float uu = -dot6(S, p);
-          sym_rank1(A, Uv, di);
-          p = p + (uu * di) * l_arr6(Uv);
-#pragma unroll
-          for (int j = 0; j < 6; j++) rt[6 * k + j] = Uv[j] * di;
-          rt[36 + k] = uu * di;
-        }
+      if (t == 0) {   // the root body: out of line, once per sweep
+        l_root_in<C>(ms, sm, flags, A, p, st);
       } else {
         // ---------------- hinge body: three dofs, last joint first
         const int d0 = lb.dofadr;
@@ -729,7 +752,7 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
           float D = lb.arm[k] + (spd ? H.h * lb.kd[k] : lD[k]);
 #pragma unroll
           for (int j = 0; j < 6; j++) D = fmaf(s[j], Uv[j], D);
-          float di = 1.0f / D, tin;
+          float di = l_rcp(D), tin;
           if (spd) {
             float q = sm[C::qpos + d + 1], qd = sm[C::qvel + d];
             if (flags & LI_INTEGRATE) {
@@ -759,9 +782,26 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
       }
       if (!spd && !resweep && dirty) st.dirty_bits |= 1u << t;
     }
-    if (!H.step_root[t]) l_rec_st_Kc<C>(w, sm, t, b, K, kc, need && b > 0, resweep);
+    if (t > 0) l_rec_st_Kc<C>(w, sm, t, b, K, kc, need, resweep);
     __syncwarp();
   }
+}
+
+// root body of the acceleration sweep: the six free-joint accelerations from the stored factors
+template <class C>
+__device__ __noinline__ S6 l_root_acc(float* sm, float* qout) {
+  const float* rt = sm + C::root;
+  const float* br = sm + C::body;
+  S6 a = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
+                   : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
+    float qdd = rt[36 + k] - dot6(l_arr6(rt + 6 * k), a);
+    qout[k] = qdd;
+    a = a + qdd * S;
+  }
+  return a;
 }
 
 // ------------------------------------------------------------------ S3: outward sweep of the accelerations + residuals of the constraint rows
@@ -779,23 +819,14 @@ __device__ __noinline__ bool l_sweep_acc(const float* ms, float* sm, const LLane
     const int b = H.sched[t][w.li];
     const bool actv = run && b >= 0;
     float K[18], kc[3];
-    if (!H.step_root[t]) l_rec_ld_Kc<C>(w, sm, t, b, K, kc);
+    if (t > 0) l_rec_ld_Kc<C>(w, sm, t, b, K, kc);
     if (actv) {
       const LBody& lb = MB[b];
       const float* br = sm + C::body + C::BODYW * b;
       S6 a;
       float qdd3[3] = {0.f, 0.f, 0.f};
-      if (b == 0) {
-        const float* rt = sm + C::root;
-        a = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-          S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
-                         : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
-          float qdd = rt[36 + k] - dot6(l_arr6(rt + 6 * k), a);
-          qout[k] = qdd;
-          a = a + qdd * S;
-        }
+      if (t == 0) {   // the root body: out of line
+        a = l_root_acc<C>(sm, qout);
         crc = false;
       } else {
         if (!(lb.flags & LB_CARRY_OUT)) { ca = ld6(sm + C::mbo + C::MBOW * lb.pmbox + LMO_A); crc = false; }
@@ -1083,6 +1114,7 @@ __device__ __noinline__ void l_substeps(const float* ms, float* sm, const LLane&
   const bool spd = (H.cfg.control_mode == SMPLSIM_CTRL_UHC_PD) && !raw, stale = H.cfg.spd_stale != 0;
   bool restore = false;   // raw mode: the caller's ctrl (kept in act) comes back the substep after an auto-reset zeroed it
   for (int s = 0; s < nsub; s++) {
+    if (H.align & 1) __syncthreads();   // keep the warps of a CTA in the same sweep: they then share the instruction-cache lines
     if (!raw) {
       if (!spd) l_torque_elem<C>(ms, sm, w, sta);
     } else if (__any_sync(L_FULL, restore)) {
@@ -1101,6 +1133,7 @@ __device__ __noinline__ void l_substeps(const float* ms, float* sm, const LLane&
     LFkOut fk = l_sweep_out<C>(ms, sm, w, f1, bad != 0);
     bool hit = false;
     fo->mask = fk.mask;
+    if (H.align & 2) __syncthreads();
     fo->iters = l_solve<C>(ms, sm, w, fk.nrows > 0, st, &hit);
     int extra = (fk.dropped ? L_ST_ROWS_DROPPED : 0) | (hit ? L_ST_MAXITER : 0);
     int badacc = l_check<C>(ms, sm, w, 1);
@@ -1122,6 +1155,7 @@ __device__ __noinline__ void l_substeps(const float* ms, float* sm, const LLane&
       for (int i = w.li; i < H.nv; i += LM_LPE) vf[i] = sm[C::qvel + i];
     }
     if (last && write_fwd) __syncwarp();   // the integration below overwrites what other lanes are still copying
+    if (H.align & 4) __syncthreads();
     if (spd && stale && (!last || prep_last)) l_sweep_in<C>(ms, sm, w, w.live, LI_SPD | LI_INTEGRATE, st);   // FK rows: s_k ; qpos / qvel: s_{k+1}
     else l_integrate<C>(ms, sm, w, st);
   }

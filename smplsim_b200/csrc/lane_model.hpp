@@ -29,7 +29,7 @@
 struct LHdr {
   int nb, nv, nu, ng, nslot, T, nmbi, nmbo;
   int obs_dim, self_obs_dim, warmset, dirtypath;
-  int bytes, body_off, geom_off, pad0;        // image size and the byte offsets of the LBody / LGeom arrays
+  int bytes, body_off, geom_off, align;       // image size and the byte offsets of the LBody / LGeom arrays
   float ls_tol, margin, mu, impratio;
   float solimp[5], imp_a, imp_b, K;
   float B, h, grav[3], plane_pos[3];
@@ -155,7 +155,9 @@ static inline std::string lane_build(const SmplsimModelDesc* s, const SmplsimEnv
         L.kp[k] = (float)s->act_kp[a]; L.kd[k] = (float)s->act_kd[a]; L.tlim[k] = (float)s->act_torque_lim[a];
         L.ascale[k] = (float)s->act_scale[a]; L.aoffset[k] = (float)s->act_offset[a];
       }
-      if (step[parent[b]] == step[b] - 1 && lane[parent[b]] == lane[b]) { L.flags |= LB_CARRY_OUT; B[parent[b]].flags |= LB_CARRY_IN; }
+      // register hand-over along a chain; never into the root: the root carries constraint rows in its subtree in nearly every
+      // substep, and a carry child would drag its whole chain into every re-sweep of the active-set iterations
+      if (parent[b] != 0 && step[parent[b]] == step[b] - 1 && lane[parent[b]] == lane[b]) { L.flags |= LB_CARRY_OUT; B[parent[b]].flags |= LB_CARRY_IN; }
     }
   }
   for (int b = 1; b < nb; b++) {
@@ -230,6 +232,6 @@ static inline std::string lane_build(const SmplsimModelDesc* s, const SmplsimEnv
   for (int k = 0; k < 6; k++) H.rarm[k] = (float)s->dof_armature[k];
   H.cfg = *cfg;
   H.obs_dim = lane_obs_dims(s, cfg, &H.self_obs_dim);
-  H.warmset = 1; H.dirtypath = 1; H.ls_tol = 1e-6f;
+  H.warmset = 1; H.dirtypath = 1; H.ls_tol = 1e-6f; H.align = 0;
   return "";
 }

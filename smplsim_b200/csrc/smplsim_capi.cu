@@ -19,7 +19,7 @@
 
 // model classes the kernels are instantiated for: <bodies, dofs, geoms, contact slots, in-mailboxes, out-mailboxes, contact
 // entries in shared memory, limit rows, records in tensor memory>
-#define L_SMPL(RECT) LCfg<24, 75, 24, 64, 4, 2, 20, 16, RECT>
+#define L_SMPL(RECT) LCfg<24, 75, 24, 64, 5, 2, 20, 16, RECT>
 #define L_SMPLX(RECT) LCfg<52, 159, 52, 128, 16, 8, 24, 24, RECT>
 
 struct SmplsimHandle {
@@ -117,6 +117,7 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   if (!why.empty()) { delete h; return fail(SMPLSIM_EUNSUPPORTED, why); }
   LHdr& H = *h->img.hdr();
   { const char* dp = std::getenv("SMPLSIM_DIRTYPATH"); if (dp) H.dirtypath = std::atoi(dp); }
+  { const char* al = std::getenv("SMPLSIM_ALIGN"); if (al) H.align = std::atoi(al); }   // CTA phase-alignment barriers (bit 0 substep, 1 solve, 2 stable-PD sweep)
   for (int b = 0; b < H.nb; b++) if (h->img.bodies()[b].ngeom > 1) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "more than one geom on a body"); }
   typedef L_SMPL(0) CS; typedef L_SMPLX(0) CX;
   if (H.nb == CS::NB && H.nv == CS::NV && H.ng <= CS::NG && H.nslot <= CS::NS && H.nmbi <= CS::NMBI && H.nmbo <= CS::NMBO) h->cls = 1;

@@ -18,15 +18,19 @@ from smplsim_b200.abi import SmplsimAuxC, SmplsimStateC, env_cfg_from, model_fro
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))
-SO = os.path.join(_HERE, "libsmplsim_emu.so")
+SO = os.environ.get("SMPLSIM_EMU_SO") or os.path.join(_HERE, "libsmplsim_emu.so")
 _L = None
 
 
 def build(force: bool = False) -> str:
     srcs = glob.glob(os.path.join(_ROOT, "smplsim_b200", "csrc", "*")) + glob.glob(os.path.join(_HERE, "*.cpp")) + glob.glob(os.path.join(_HERE, "shim", "*"))
     newest = max(os.path.getmtime(s) for s in srcs)
+    if "SMPLSIM_EMU_SO" in os.environ:
+        return SO
     if force or not os.path.exists(SO) or os.path.getmtime(SO) < newest:
-        cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas", "-I", os.path.join(_HERE, "shim"),
+        # nvcc contracts a * b + c into FFMA; do the same where the host has FMA so that the rounding pattern is comparable
+        fma = ["-mfma", "-ffp-contract=fast"] if "fma" in open("/proc/cpuinfo").read() else ["-ffp-contract=off"]
+        cmd = ["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", *fma, "-Wno-unknown-pragmas", "-I", os.path.join(_HERE, "shim"),
                "-x", "c++", os.path.join(_ROOT, "smplsim_b200", "csrc", "smplsim_capi.cu"), "-x", "c++", os.path.join(_HERE, "emu.cpp"), "-o", SO]
         subprocess.check_call(cmd)
     return SO
