@@ -59,6 +59,7 @@ struct LCfg {
 // misc words
 #define LMI_NCON 0
 #define LMI_NLIM 1
+#define LMI_DISP 2   // root displacement x, y accumulated over the substeps of this call (words 2, 3)
 // task words (as in round 1)
 #define L_TSK_CHANGE 4
 #define L_TSK_CURT 5
@@ -94,6 +95,7 @@ struct LLane {
   int gbase;       // first lane of the group
   unsigned gmask;  // warp mask of this env's lanes
   bool live;
+  bool bar;        // CTA barriers are legal here (every warp of the CTA makes this call); false inside warp-divergent redo paths
   int env;
   unsigned tm;     // tensor-memory address of this warp's record block (RECT = 1)
   float* gscr;     // overflow contact entries of this env (global scratch)
@@ -180,6 +182,8 @@ static inline uint32_t* emu_tm(unsigned a) {
 #define L_TM_WAIT_LD() do { } while (0)
 #define L_TM_WAIT_ST() do { } while (0)
 static inline unsigned __float_as_uint(float f) { return emu_bits(f); }
+static inline int __float_as_int(float f) { return (int)emu_bits(f); }
+static inline float __int_as_float(int i) { return emu_float((unsigned)i); }
 static inline float __uint_as_float(unsigned u) { return emu_float(u); }
 #endif
 
@@ -332,43 +336,253 @@ __device__ __forceinline__ int l_gscan(int v, const LLane& w, int* total) {
   return inc - v;
 }
 
-// root body of the outward sweep (free joint, lane 0 of the group at step 0): stable-PD acceleration of the six root dofs from
-// the stored factors, then pose / velocity / bias acceleration of the state in qpos, qvel
-template <class C>
-__device__ __noinline__ void l_root_out(const float* ms, float* sm, int flags, Q4& cq, V3& cx, S6& cv, S6& cab, S6& casp) {
-  const LHdr& H = l_hdr<C>(ms);
-  float* br = sm + C::body;
-  float* qpos = sm + C::qpos;
-  const float* qvel = sm + C::qvel;
-  if (flags & LF_GOUT) {      // old rotation columns (FK rows of the last forward pass)
-    const float* rt = sm + C::root;
-    S6 a = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+// ------------------------------------------------------------------ vectorised shared-memory rows (all rows are 16-byte aligned)
+__device__ __forceinline__ void l_ld12(const float* p, float* o) {
+  const float4* q = (const float4*)p;
+  float4 a = q[0], b = q[1], c = q[2];
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w; o[8] = c.x; o[9] = c.y; o[10] = c.z; o[11] = c.w;
+}
+__device__ __forceinline__ void l_st12(float* p, const float* o) {
+  float4* q = (float4*)p;
+  q[0] = make_float4(o[0], o[1], o[2], o[3]); q[1] = make_float4(o[4], o[5], o[6], o[7]); q[2] = make_float4(o[8], o[9], o[10], o[11]);
+}
+// body row words 12..23: rigid inertia (10), contact / limit-row info, spare
+__device__ __forceinline__ int l_ld_r10(const float* br, float* r10) {
+  float t[12];
+  l_ld12(br + LBR_R10, t);
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-      S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
-                     : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
-      float qdd = rt[36 + k] - dot6(l_arr6(rt + 6 * k), a);
-      a = a + qdd * S;
+  for (int j = 0; j < 10; j++) r10[j] = t[j];
+  return __float_as_int(t[10]);
+}
+// in-mailbox: [IA 21 | pA 6 | dirty]
+__device__ __forceinline__ bool l_mbi_add(const float* mi, float* A, S6& p) {
+  const float4* q = (const float4*)mi;
+  float4 v0 = q[0], v1 = q[1], v2 = q[2], v3_ = q[3], v4 = q[4], v5 = q[5], v6 = q[6];
+  A[0] += v0.x; A[1] += v0.y; A[2] += v0.z; A[3] += v0.w; A[4] += v1.x; A[5] += v1.y; A[6] += v1.z; A[7] += v1.w;
+  A[8] += v2.x; A[9] += v2.y; A[10] += v2.z; A[11] += v2.w; A[12] += v3_.x; A[13] += v3_.y; A[14] += v3_.z; A[15] += v3_.w;
+  A[16] += v4.x; A[17] += v4.y; A[18] += v4.z; A[19] += v4.w; A[20] += v5.x;
+  p.a.x += v5.y; p.a.y += v5.z; p.a.z += v5.w; p.l.x += v6.x; p.l.y += v6.y; p.l.z += v6.z;
+  return __float_as_int(v6.w) != 0;
+}
+__device__ __forceinline__ void l_mbi_put(float* mi, const float* A, S6 p, bool dirty) {
+  float4* q = (float4*)mi;
+  q[0] = make_float4(A[0], A[1], A[2], A[3]); q[1] = make_float4(A[4], A[5], A[6], A[7]); q[2] = make_float4(A[8], A[9], A[10], A[11]);
+  q[3] = make_float4(A[12], A[13], A[14], A[15]); q[4] = make_float4(A[16], A[17], A[18], A[19]);
+  q[5] = make_float4(A[20], p.a.x, p.a.y, p.a.z); q[6] = make_float4(p.l.x, p.l.y, p.l.z, __int_as_float(dirty ? 1 : 0));
+}
+// out-mailbox pose part [quat 4 | xpos 3 | - | v 6 | ab 6] (words 0..19) and acceleration part (words 20..25)
+struct LPose { Q4 q; V3 x; S6 v, ab; };
+__device__ __forceinline__ void l_mbo_put_pose(float* mo, const LPose& P) {
+  float4* q = (float4*)mo;
+  q[0] = make_float4(P.q.w, P.q.x, P.q.y, P.q.z); q[1] = make_float4(P.x.x, P.x.y, P.x.z, 0.f);
+  q[2] = make_float4(P.v.a.x, P.v.a.y, P.v.a.z, P.v.l.x); q[3] = make_float4(P.v.l.y, P.v.l.z, P.ab.a.x, P.ab.a.y);
+  q[4] = make_float4(P.ab.a.z, P.ab.l.x, P.ab.l.y, P.ab.l.z);
+}
+__device__ __forceinline__ void l_mbo_get_pose(const float* mo, LPose& P) {
+  const float4* q = (const float4*)mo;
+  float4 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4];
+  P.q.w = a.x; P.q.x = a.y; P.q.y = a.z; P.q.z = a.w; P.x = v3(b.x, b.y, b.z);
+  P.v = s6(v3(c.x, c.y, c.z), v3(c.w, d.x, d.y)); P.ab = s6(v3(d.z, d.w, e.x), v3(e.y, e.z, e.w));
+}
+__device__ __forceinline__ void l_mbo_put_acc(float* mo, S6 a) {
+  ((float4*)mo)[5] = make_float4(a.a.x, a.a.y, a.a.z, a.l.x);
+  mo[24] = a.l.y; mo[25] = a.l.z;
+}
+__device__ __forceinline__ S6 l_mbo_get_acc(const float* mo) {
+  float4 a = ((const float4*)mo)[5];
+  return s6(v3(a.x, a.y, a.z), v3(a.w, mo[24], mo[25]));
+}
+// joint axes + body position of a body row (words 0..11)
+struct LAxes { V3 a0, a1, a2, x; };
+__device__ __forceinline__ LAxes l_ld_axes(const float* br) {
+  float t[12];
+  l_ld12(br, t);
+  LAxes r; r.a0 = v3(t[0], t[1], t[2]); r.a1 = v3(t[3], t[4], t[5]); r.a2 = v3(t[6], t[7], t[8]); r.x = v3(t[9], t[10], t[11]);
+  return r;
+}
+__device__ __forceinline__ V3 l_axis(const LAxes& X, int k) { return k == 0 ? X.a0 : k == 1 ? X.a1 : X.a2; }
+
+// residuals rs = J a - aref of the body's contact rows at acceleration a; returns "sign pattern == working set"
+template <class C>
+__device__ __forceinline__ bool l_rows_eval(const LHdr& H, float* sm, const LLane& w, int cb, int cn, S6 a) {
+  bool same = true;
+  for (int c = cb; c < cb + cn; c++) {
+    float* ce = (c < C::NCS) ? nullptr : w.gscr + (size_t)C::CONW * (c - C::NCS);
+    float e[12];
+    if (c < C::NCS) l_ld12(sm + C::con + C::CONW * c, e);
+    else for (int j = 0; j < 12; j++) e[j] = ce[j];
+    const int info = __float_as_int(e[0]);
+    if (!(info & 1)) continue;
+    V3 cpt = v3(e[1], e[2], e[3]), t1 = v3(e[4], e[5], e[6]);
+    int nf = 0;
+    float rs[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      rs[k] = dot6(l_wrench(H, cpt, t1, k), a) - e[8 + k];
+      if (rs[k] < 0.f) nf |= 2 << k;
     }
-    casp = a;
+    if (c < C::NCS) ((float4*)(sm + C::con + C::CONW * c))[LCE_RS / 4] = make_float4(rs[0], rs[1], rs[2], rs[3]);
+    else for (int k = 0; k < 4; k++) ce[LCE_RS + k] = rs[k];
+    if (nf != (info & 30)) same = false;
   }
-  if (flags & LF_FK) {
-    Q4 qc;
-    qc.w = qpos[3]; qc.x = qpos[4]; qc.y = qpos[5]; qc.z = qpos[6];
-    qc = qnormalize(qc);
-    qpos[3] = qc.w; qpos[4] = qc.x; qpos[5] = qc.y; qpos[6] = qc.z;
-    float R[9];
-    q2mat(qc, R);
-    V3 c0 = v3(R[0], R[3], R[6]), c1 = v3(R[1], R[4], R[7]), c2 = v3(R[2], R[5], R[8]);
-    st3(br + LBR_AX, c0); st3(br + LBR_AX + 3, c1); st3(br + LBR_AX + 6, c2);
-    st3(br + LBR_X, v3(0.f, 0.f, 0.f));
-    cq = qc; cx = v3(0.f, 0.f, 0.f);
-    if (flags & LF_VEL) {
-      V3 vl = ld3(qvel), wv = qvel[3] * c0 + qvel[4] * c1 + qvel[5] * c2;
-      cv = s6(wv, vl);
-      cab = s6(v3(0.f, 0.f, 0.f), v3(-H.grav[0], -H.grav[1], -H.grav[2]) + cross(vl, wv));
+  return same;
+}
+
+// rigid inertia, bias force, sensors, xquat of the body whose pose is P; returns pb
+template <class C>
+__device__ __forceinline__ S6 l_body_post(const LBody& lb, float* sm, const LLane& w, int b, int flags, const LPose& P, float* br, int ci) {
+  S6 pbv = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+  if (flags & LF_VEL) {
+    float t[12];
+    l_rigid10(lb, P.q, P.x, t);
+    t[10] = __int_as_float(ci); t[11] = 0.f;
+    l_st12(br + LBR_R10, t);
+    pbv = rb_mul(t, P.ab) + cross_force(P.v, rb_mul(t, P.v));
+    if ((flags & LF_SENS) && w.gsens) {
+      st3(w.gsens + 6 * b, P.v.l + cross(P.v.a, P.x));
+      st3(w.gsens + 6 * b + 3, P.v.a);
     }
   }
+  if (flags & LF_XQUAT) ((float4*)(sm + C::xq))[b] = make_float4(P.q.w, P.q.x, P.q.y, P.q.z);
+  return pbv;
+}
+
+// broad phase of the body's geom against the floor: number of contact entries to reserve (exact: > 0 iff at least one contact)
+struct LGeomCtx { float R[9]; V3 c, ax; float d0, na; };
+__device__ __forceinline__ int l_broad(const LHdr& H, const LGeom& G, const LPose& P, float h0, LGeomCtx& X) {
+  const V3 pn = ld3(H.plane_n);
+  q2mat(P.q, X.R);
+  X.c = P.x + mrot(X.R, ld3(G.pos));
+  X.d0 = h0 + dot(pn, X.c);
+  X.ax = v3(0.f, 0.f, 0.f); X.na = 0.f;
+  if (G.type == SMPLSIM_GEOM_BOX) {
+    float ext = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) ext += fabsf(dot(pn, mrot(X.R, v3(G.mat[j], G.mat[3 + j], G.mat[6 + j])))) * G.size[j];
+    return (X.d0 - ext <= H.margin) ? 4 : 0;
+  }
+  X.ax = mrot(X.R, v3(G.mat[2], G.mat[5], G.mat[8]));
+  X.na = dot(pn, X.ax);
+  float hl = (G.type == SMPLSIM_GEOM_CAPSULE) ? G.size[1] : 0.f;
+  return (X.d0 - hl * fabsf(X.na) - G.size[0] <= H.margin) ? ((G.type == SMPLSIM_GEOM_CAPSULE) ? 2 : 1) : 0;
+}
+
+// narrow phase (plane vs box corners / capsule ends / sphere) into the reserved entries [cb, cb + alloc); returns
+// the number of contacts
+template <class C>
+__device__ __forceinline__ int l_narrow(const LHdr& H, const LGeom& G, int g, const LGeomCtx& X, S6 vb, float tiw0, float* sm, const LLane& w, int cb, int alloc) {
+  const V3 pn = ld3(H.plane_n);
+  const unsigned char* pf = (const unsigned char*)(sm + C::pfl);
+  V3 t1 = ld3(H.t1_default);
+  int cnt = 0;
+  const int npt = (G.type == SMPLSIM_GEOM_BOX) ? 8 : alloc;
+  if (G.type == SMPLSIM_GEOM_CAPSULE) {
+    t1 = X.ax - X.na * pn;
+    float nn = sqrtf(dot(t1, t1));
+    t1 = (nn < 1e-15f) ? v3(1.f, 0.f, 0.f) : (1.0f / nn) * t1;
+  }
+#pragma unroll 1
+  for (int i = 0; i < npt && cnt < alloc; i++) {
+    V3 cp; float dist;
+    if (G.type == SMPLSIM_GEOM_BOX) {
+      V3 vl = v3((i & 1) ? G.size[0] : -G.size[0], (i & 2) ? G.size[1] : -G.size[1], (i & 4) ? G.size[2] : -G.size[2]);
+      V3 wv = mrot(X.R, mrot(G.mat, vl));
+      float l = dot(pn, wv);
+      if (X.d0 + l > H.margin || l > 0.f) continue;
+      dist = X.d0 + l;
+      cp = X.c + wv - (0.5f * dist) * pn;
+    } else {
+      float hl = (G.type == SMPLSIM_GEOM_CAPSULE) ? G.size[1] : 0.f, sg = i ? -hl : hl;
+      dist = X.d0 + sg * X.na - G.size[0];
+      if (dist > H.margin) continue;
+      cp = X.c + sg * X.ax - (G.size[0] + 0.5f * dist) * pn;
+    }
+    float pm = dist - H.margin, imp = l_impedance(H, pm);
+    float R0 = fmaxf((1.f - imp) / imp * (tiw0 + H.mu * H.mu * tiw0), 1e-15f);
+    float R1 = R0 / fmaxf(H.impratio, 1e-15f), mu = H.mu * sqrtf(R1 / R0);
+    float kterm = H.K * imp * pm;
+    // working set inherited from the slot's previous substep; new contacts start with all four rows active
+    int slot = G.slot0 + cnt, pv = pf[slot];
+    float e[12];
+    e[0] = __int_as_float(1 | ((pv & 1) ? (pv & 30) : 30) | (g << 8) | (slot << 16));
+    e[1] = cp.x; e[2] = cp.y; e[3] = cp.z; e[4] = t1.x; e[5] = t1.y; e[6] = t1.z;
+    e[7] = 1.0f / (2.f * mu * mu * R0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) e[8 + k] = -H.B * dot6(l_wrench(H, cp, t1, k), vb) - kterm;
+    const int c = cb + cnt;
+    if (c < C::NCS) l_st12(sm + C::con + C::CONW * c, e);
+    else { float* ce = w.gscr + (size_t)C::CONW * (c - C::NCS); for (int j = 0; j < 12; j++) ce[j] = e[j]; }
+    cnt++;
+  }
+  for (int i = cnt; i < alloc; i++) {
+    const int c = cb + i;
+    if (c < C::NCS) ((int*)(sm + C::con + C::CONW * c))[LCE_INFO] = 0;
+    else ((int*)(w.gscr + (size_t)C::CONW * (c - C::NCS)))[LCE_INFO] = 0;
+  }
+  return cnt;
+}
+
+// root body of the outward sweep (free joint; lane 0 of the group, step 0; every lane makes the call): stable-PD
+// acceleration of the six root dofs from the stored factors, pose / velocity / bias acceleration of the state in qpos, qvel,
+// rigid inertia, bias force, contacts of the root's geom.  Children read the pose from the root's out-mailbox.
+struct LRootOut { int ncon, npresent; unsigned long long gbits; };
+template <class C>
+__device__ __noinline__ LRootOut l_root_out(const float* ms, float* sm, const LLane& w, int flags, float h0) {
+  const LHdr& H = l_hdr<C>(ms);
+  const LBody& lb = l_bodies(ms)[0];
+  LRootOut R; R.ncon = 0; R.npresent = 0; R.gbits = 0ull;
+  const bool actv = w.live && w.li == 0;
+  S6 pbv = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+  int alloc = 0;
+  if (actv) {
+    float* br = sm + C::body;
+    float* mo = sm + C::mbo + C::MBOW * lb.out_mbox;
+    float* qpos = sm + C::qpos;
+    const float* qvel = sm + C::qvel;
+    if (flags & LF_GOUT) {      // old rotation columns (FK rows of the last forward pass)
+      const float* rt = sm + C::root;
+      S6 a = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
+                       : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
+        float qdd = rt[36 + k] - dot6(l_arr6(rt + 6 * k), a);
+        a = a + qdd * S;
+      }
+      l_mbo_put_acc(mo, a);
+    }
+    if (flags & LF_FK) {
+      LPose P;
+      P.q.w = qpos[3]; P.q.x = qpos[4]; P.q.y = qpos[5]; P.q.z = qpos[6];
+      P.q = qnormalize(P.q);
+      qpos[3] = P.q.w; qpos[4] = P.q.x; qpos[5] = P.q.y; qpos[6] = P.q.z;
+      float Rm[9];
+      q2mat(P.q, Rm);
+      V3 c0 = v3(Rm[0], Rm[3], Rm[6]), c1 = v3(Rm[1], Rm[4], Rm[7]), c2 = v3(Rm[2], Rm[5], Rm[8]);
+      st3(br + LBR_AX, c0); st3(br + LBR_AX + 3, c1); st3(br + LBR_AX + 6, c2);
+      P.x = v3(0.f, 0.f, 0.f);
+      st3(br + LBR_X, P.x);
+      P.v = s6(P.x, P.x); P.ab = P.v;
+      if (flags & LF_VEL) {
+        V3 vl = ld3(qvel), wv = qvel[3] * c0 + qvel[4] * c1 + qvel[5] * c2;
+        P.v = s6(wv, vl);
+        P.ab = s6(v3(0.f, 0.f, 0.f), v3(-H.grav[0], -H.grav[1], -H.grav[2]) + cross(vl, wv));
+      }
+      l_mbo_put_pose(mo, P);
+      LGeomCtx X;
+      if ((flags & LF_COLLIDE) && lb.ngeom > 0) alloc = l_broad(H, l_geoms(ms)[lb.geom0], P, h0, X);
+      pbv = l_body_post<C>(lb, sm, w, 0, flags, P, br, alloc << 8);
+      if (alloc) {
+        int cnt = l_narrow<C>(H, l_geoms(ms)[lb.geom0], lb.geom0, X, P.v, lb.tiw0, sm, w, 0, alloc);
+        if (cnt) R.gbits = 1ull << (lb.geom0 + 1);
+        R.npresent = cnt;
+      }
+    }
+  }
+  if (flags & LF_VEL) l_rec_st_pb<C>(w, sm, 0, 0, pbv, actv);
+  R.ncon = __shfl_sync(L_FULL, alloc, w.gbase);
+  __syncwarp();
+  return R;
 }
 
 template <class C>
@@ -376,222 +590,134 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
   const LHdr& H = l_hdr<C>(ms);
   const LBody* MB = l_bodies(ms);
   const LGeom* MG = l_geoms(ms);
-  Q4 cq; cq.w = 1.f; cq.x = cq.y = cq.z = 0.f;
-  V3 cx = v3(0.f, 0.f, 0.f);
-  S6 cv = s6(cx, cx), cab = cv, casp = cv;
-  int ncon = 0, nlim = 0, npresent = 0, dropped = 0;
-  unsigned long long gbits = 0ull;
-  const V3 pn = ld3(H.plane_n);
-  const float h0 = dot(pn, ld3(sm + C::qpos) - ld3(H.plane_pos));
+  const float h0 = dot(ld3(H.plane_n), ld3(sm + C::qpos) - ld3(H.plane_pos));
+  LRootOut R0 = l_root_out<C>(ms, sm, w, flags, h0);
+  LPose P;   // pose / velocity / bias acceleration handed down the lane's chain
+  P.q.w = 1.f; P.q.x = P.q.y = P.q.z = 0.f; P.x = v3(0.f, 0.f, 0.f); P.v = s6(P.x, P.x); P.ab = P.v;
+  S6 casp = P.v;
+  int ncon = R0.ncon, nlim = 0, npresent = R0.npresent, dropped = 0;
+  unsigned long long gbits = R0.gbits;
   const bool spd_torque = (flags & LF_GOUT) && H.cfg.control_mode == SMPLSIM_CTRL_UHC_PD;
-  for (int t = 0; t < H.T; t++) {
+  const bool stepbar = (H.align & 16) && w.bar;
+  for (int t = 1; t < H.T; t++) {
+    if (stepbar) __syncthreads();
     const int b = H.sched[t][w.li];
     const bool actv = w.live && b >= 0;
     float K[18], kc[3];
-    if ((flags & LF_GOUT) && t > 0) l_rec_ld_Kc<C>(w, sm, t, b, K, kc);
+    if (flags & LF_GOUT) l_rec_ld_Kc<C>(w, sm, t, b, K, kc);
     S6 pbv = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
     float* br = sm + C::body + C::BODYW * (actv ? b : 0);
-    int alloc = 0, nlr = 0, g = 0;   // contact entries / limit rows this lane wants; its geom
-    float gd0 = 0.f, gna = 0.f, tiw0 = 0.f;
-    V3 gc = cx, gax = cx;
-    float gR[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) gR[i] = 0.f;
-    S6 vb = cv;
+    int alloc = 0, nlr = 0;   // contact entries / limit rows this lane wants
+    LGeomCtx X;
     if (actv) {
       const LBody& lb = MB[b];
-      Q4 qc; V3 x; S6 v, ab;
-      if (t == 0) {   // the root body (free joint): out of line, once per sweep
-        l_root_out<C>(ms, sm, flags, cq, cx, cv, cab, casp);
-        qc = cq; x = cx; v = cv; ab = cab;
-      } else {
-        // ---------------- hinge body
-        const int d0 = lb.dofadr;
-        if (!(lb.flags & LB_CARRY_OUT)) {   // junction: the parent's lane left its state in the mailbox
-          const float* mo = sm + C::mbo + C::MBOW * lb.pmbox;
-          cq.w = mo[LMO_Q]; cq.x = mo[LMO_Q + 1]; cq.y = mo[LMO_Q + 2]; cq.z = mo[LMO_Q + 3];
-          cx = ld3(mo + LMO_X); cv = ld6(mo + LMO_V); cab = ld6(mo + LMO_AB); casp = ld6(mo + LMO_A);
-        }
-        if (flags & LF_GOUT) {
-          // stable-PD acceleration of this body's dofs: qdd_k = c_k - K_k . a  (old joint axes / position)
-          S6 a = casp;
+      const int d0 = lb.dofadr;
+      if (!(lb.flags & LB_CARRY_OUT)) {   // junction: the parent's lane left its state in the mailbox
+        const float* mo = sm + C::mbo + C::MBOW * lb.pmbox;
+        if (flags & LF_FK) l_mbo_get_pose(mo, P);
+        if (flags & LF_GOUT) casp = l_mbo_get_acc(mo);
+      }
+      const float q0 = sm[C::qpos + d0 + 1], q1 = sm[C::qpos + d0 + 2], q2 = sm[C::qpos + d0 + 3];
+      const float qd0 = sm[C::qvel + d0], qd1 = sm[C::qvel + d0 + 1], qd2 = sm[C::qvel + d0 + 2];
+      if (flags & LF_GOUT) {
+        // stable-PD acceleration of this body's dofs: qdd_k = c_k - K_k . a  (joint axes / position of the last forward pass)
+        const LAxes AX = l_ld_axes(br);
+        S6 a = casp;
 #pragma unroll
-          for (int k = 0; k < 3; k++) {
-            S6 S = l_hingeS(br, k);
-            float qdd = kc[k] - dot6(l_arr6(K + 6 * k), a);
-            a = a + qdd * S;
-            if (spd_torque) {      // controllers.py:165-190 with the acceleration already solved: tau = -kp (q + qd h - tgt) - kd (qd + qdd h)
-              int d = d0 + k, i = d - 6;
-              float tgt = fmaf(sm[C::act + i], lb.ascale[k], lb.aoffset[k]), q = sm[C::qpos + d + 1], qd = sm[C::qvel + d];
-              float tq = -lb.kp[k] * (q + qd * H.h - tgt) - lb.kd[k] * (qd + qdd * H.h);
-              tq = fminf(fmaxf(tq, -lb.tlim[k]), lb.tlim[k]);
-              sm[C::tau + i] = ztau ? 0.f : tq;
-            }
+        for (int k = 0; k < 3; k++) {
+          V3 ax = l_axis(AX, k);
+          S6 S = s6(ax, cross(AX.x, ax));
+          float qdd = kc[k] - dot6(l_arr6(K + 6 * k), a);
+          a = a + qdd * S;
+          if (spd_torque) {      // controllers.py:165-190 with the acceleration already solved: tau = -kp (q + qd h - tgt) - kd (qd + qdd h)
+            const int i = d0 + k - 6;
+            float q = k == 0 ? q0 : k == 1 ? q1 : q2, qd = k == 0 ? qd0 : k == 1 ? qd1 : qd2;
+            float tgt = fmaf(sm[C::act + i], lb.ascale[k], lb.aoffset[k]);
+            float tq = -lb.kp[k] * (q + qd * H.h - tgt) - lb.kd[k] * (qd + qdd * H.h);
+            tq = fminf(fmaxf(tq, -lb.tlim[k]), lb.tlim[k]);
+            sm[C::tau + i] = ztau ? 0.f : tq;
           }
-          casp = a;
         }
-        qc = cq; x = cx; v = cv; ab = cab;
-        if (flags & LF_FK) {
-          float Rp[9];
-          q2mat(cq, Rp);
-          x = cx + mrot(Rp, ld3(lb.bpos));
-          Q4 qb; qb.w = lb.bquat[0]; qb.x = lb.bquat[1]; qb.y = lb.bquat[2]; qb.z = lb.bquat[3];
-          qc = qmul(cq, qb);
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            int d = d0 + k;
-            V3 al = ld3(lb.axis + 3 * k);
-            V3 a = qrot(qc, al);
-            st3(br + LBR_AX + 3 * k, a);
-            if (flags & LF_VEL) {
-              S6 S = s6(a, cross(x, a));
-              float qd = sm[C::qvel + d];
-              ab = ab + qd * cross_motion(v, S);
-              v = v + qd * S;
-            }
-            float sn, cs;
-            l_sincos(0.5f * sm[C::qpos + d + 1], &sn, &cs);
-            Q4 qj; qj.w = cs; qj.x = al.x * sn; qj.y = al.y * sn; qj.z = al.z * sn;
-            qc = qmul(qc, qj);
-          }
-          qc = qnormalize(qc);
-          st3(br + LBR_X, x);
-        }
+        casp = a;
+        if (lb.out_mbox >= 0) l_mbo_put_acc(sm + C::mbo + C::MBOW * lb.out_mbox, casp);
       }
       if (flags & LF_FK) {
-        if (flags & LF_VEL) {
-          float r10[10];
-          l_rigid10(lb, qc, x, r10);
+        float Rp[9], row[12];
+        q2mat(P.q, Rp);
+        V3 x = P.x + mrot(Rp, ld3(lb.bpos));
+        Q4 qb; qb.w = lb.bquat[0]; qb.x = lb.bquat[1]; qb.y = lb.bquat[2]; qb.z = lb.bquat[3];
+        Q4 qc = qmul(P.q, qb);
+        S6 v = P.v, ab = P.ab;
 #pragma unroll
-          for (int j = 0; j < 10; j++) br[LBR_R10 + j] = r10[j];
-          pbv = rb_mul(r10, ab) + cross_force(v, rb_mul(r10, v));
-          if ((flags & LF_SENS) && w.gsens) {
-            st3(w.gsens + 6 * b, v.l + cross(v.a, x));
-            st3(w.gsens + 6 * b + 3, v.a);
+        for (int k = 0; k < 3; k++) {
+          V3 al = ld3(lb.axis + 3 * k);
+          V3 a = qrot(qc, al);
+          row[3 * k] = a.x; row[3 * k + 1] = a.y; row[3 * k + 2] = a.z;
+          if (flags & LF_VEL) {
+            S6 S = s6(a, cross(x, a));
+            float qd = k == 0 ? qd0 : k == 1 ? qd1 : qd2;
+            ab = ab + qd * cross_motion(v, S);
+            v = v + qd * S;
           }
+          float sn, cs;
+          l_sincos(0.5f * (k == 0 ? q0 : k == 1 ? q1 : q2), &sn, &cs);
+          Q4 qj; qj.w = cs; qj.x = al.x * sn; qj.y = al.y * sn; qj.z = al.z * sn;
+          qc = qmul(qc, qj);
         }
-        if (flags & LF_XQUAT) { float* xq = sm + C::xq + 4 * b; xq[0] = qc.w; xq[1] = qc.x; xq[2] = qc.y; xq[3] = qc.z; }
-        cq = qc; cx = x; cv = v; cab = ab;
-      }
-      if (lb.out_mbox >= 0) {
-        float* mo = sm + C::mbo + C::MBOW * lb.out_mbox;
-        if (flags & LF_FK) {
-          mo[LMO_Q] = cq.w; mo[LMO_Q + 1] = cq.x; mo[LMO_Q + 2] = cq.y; mo[LMO_Q + 3] = cq.z;
-          st3(mo + LMO_X, cx); st6(mo + LMO_V, cv); st6(mo + LMO_AB, cab);
-        }
-        if (flags & LF_GOUT) st6(mo + LMO_A, casp);
-      }
-      vb = cv;
-      if (flags & LF_COLLIDE) {
-        // ---------------- broad phase of the body's geom: how many contact entries to reserve
-        if (lb.ngeom > 0) {
-          g = lb.geom0;
-          const LGeom& G = MG[g];
-          q2mat(cq, gR);
-          gc = cx + mrot(gR, ld3(G.pos));
-          gd0 = h0 + dot(pn, gc);
-          tiw0 = lb.tiw0;
-          if (G.type == SMPLSIM_GEOM_BOX) {
-            float ext = 0.f;
-#pragma unroll
-            for (int j = 0; j < 3; j++) ext += fabsf(dot(pn, mrot(gR, v3(G.mat[j], G.mat[3 + j], G.mat[6 + j])))) * G.size[j];
-            alloc = (gd0 - ext <= H.margin) ? 4 : 0;
-          } else {
-            gax = mrot(gR, v3(G.mat[2], G.mat[5], G.mat[8]));
-            gna = dot(pn, gax);
-            float hl = (G.type == SMPLSIM_GEOM_CAPSULE) ? G.size[1] : 0.f;
-            alloc = (gd0 - hl * fabsf(gna) - G.size[0] <= H.margin) ? ((G.type == SMPLSIM_GEOM_CAPSULE) ? 2 : 1) : 0;
-          }
-        }
-        if (b > 0) {
+        qc = qnormalize(qc);
+        row[9] = x.x; row[10] = x.y; row[11] = x.z;
+        l_st12(br, row);
+        P.q = qc; P.x = x; P.v = v; P.ab = ab;
+        if (lb.out_mbox >= 0) l_mbo_put_pose(sm + C::mbo + C::MBOW * lb.out_mbox, P);
+        if (flags & LF_COLLIDE) {
+          if (lb.ngeom > 0) alloc = l_broad(H, MG[lb.geom0], P, h0, X);
 #pragma unroll
           for (int k = 0; k < 3; k++) {
-            float q = sm[C::qpos + lb.dofadr + k + 1];
+            float q = k == 0 ? q0 : k == 1 ? q1 : q2;
             if (((lb.limited >> k) & 1) && (q - lb.rlo[k] < 0.f || lb.rhi[k] - q < 0.f)) nlr++;
           }
         }
       }
     }
-    if (flags & LF_VEL) l_rec_st_pb<C>(w, sm, t, b, pbv, actv);
+    int cb = 0, lbs = 0, lcnt = 0;
     if (flags & LF_COLLIDE) {
       // ---------------- reserve list space: deterministic order (step, lane)
       int tot, ex = l_gscan(alloc | (nlr << 8), w, &tot);
-      int cb = ncon + (ex & 255), lbs = nlim + (ex >> 8);
+      cb = ncon + (ex & 255); lbs = nlim + (ex >> 8);
       ncon += tot & 255; nlim += tot >> 8;
-      if (actv) {
-        const LBody& lb = MB[b];
-        int lcnt = nlr;
-        if (lbs + nlr > C::NLS) { lcnt = max(0, C::NLS - lbs); dropped = 1; }
-        ((int*)br)[LBR_CI] = cb | (alloc << 8) | (lbs << 16) | (lcnt << 24);
-        if (alloc) {
-          // ---------------- narrow phase (plane vs box corners / capsule ends / sphere), SURVEY A.5
-          const LGeom& G = MG[g];
-          unsigned char* pf = (unsigned char*)(sm + C::pfl);
-          V3 t1 = ld3(H.t1_default);
-          int cnt = 0;
-          const int npt = (G.type == SMPLSIM_GEOM_BOX) ? 8 : alloc;
-          if (G.type == SMPLSIM_GEOM_CAPSULE) {
-            t1 = gax - gna * pn;
-            float nn = sqrtf(dot(t1, t1));
-            t1 = (nn < 1e-15f) ? v3(1.f, 0.f, 0.f) : (1.0f / nn) * t1;
-          }
-#pragma unroll 1
-          for (int i = 0; i < npt && cnt < alloc; i++) {
-            V3 cp; float dist;
-            if (G.type == SMPLSIM_GEOM_BOX) {
-              V3 vl = v3((i & 1) ? G.size[0] : -G.size[0], (i & 2) ? G.size[1] : -G.size[1], (i & 4) ? G.size[2] : -G.size[2]);
-              V3 wv = mrot(gR, mrot(G.mat, vl));
-              float l = dot(pn, wv);
-              if (gd0 + l > H.margin || l > 0.f) continue;
-              dist = gd0 + l;
-              cp = gc + wv - (0.5f * dist) * pn;
-            } else {
-              float hl = (G.type == SMPLSIM_GEOM_CAPSULE) ? G.size[1] : 0.f, sg = i ? -hl : hl;
-              dist = gd0 + sg * gna - G.size[0];
-              if (dist > H.margin) continue;
-              cp = gc + sg * gax - (G.size[0] + 0.5f * dist) * pn;
-            }
-            float* ce = l_centry<C>(sm, w, cb + cnt);
-            float pm = dist - H.margin, imp = l_impedance(H, pm);
-            float R0 = fmaxf((1.f - imp) / imp * (tiw0 + H.mu * H.mu * tiw0), 1e-15f);
-            float R1 = R0 / fmaxf(H.impratio, 1e-15f), mu = H.mu * sqrtf(R1 / R0);
-            float kterm = H.K * imp * pm;
-            st3(ce + LCE_CP, cp); st3(ce + LCE_T1, t1);
-            ce[LCE_D] = 1.0f / (2.f * mu * mu * R0);
+      lcnt = nlr;
+      if (lbs + nlr > C::NLS) { lcnt = max(0, C::NLS - lbs); if (nlr) dropped = 1; }
+    }
+    if (actv && (flags & LF_FK)) {
+      const LBody& lb = MB[b];
+      pbv = l_body_post<C>(lb, sm, w, b, flags, P, br, cb | (alloc << 8) | (lbs << 16) | (lcnt << 24));
+      if (alloc) {
+        int cnt = l_narrow<C>(H, MG[lb.geom0], lb.geom0, X, P.v, lb.tiw0, sm, w, cb, alloc);
+        if (cnt) gbits |= 1ull << (lb.geom0 + 1);
+        npresent += cnt;
+      }
+      if (lcnt) {
+        int e = lbs;
 #pragma unroll
-            for (int k = 0; k < 4; k++) ce[LCE_AREF + k] = -H.B * dot6(l_wrench(H, cp, t1, k), vb) - kterm;
-            // working set inherited from the slot's previous substep; new contacts start with all four rows active
-            int slot = G.slot0 + cnt, pv = pf[slot];
-            ((int*)ce)[LCE_INFO] = 1 | ((pv & 1) ? (pv & 30) : 30) | (g << 8) | (slot << 16);
-            cnt++;
-          }
-          for (int i = cnt; i < alloc; i++) ((int*)l_centry<C>(sm, w, cb + i))[LCE_INFO] = 0;
-          if (cnt) gbits |= 1ull << (g + 1);
-          npresent += cnt;
+        for (int k = 0; k < 3; k++) {
+          int d = lb.dofadr + k;
+          float q = sm[C::qpos + d + 1], dlo = q - lb.rlo[k], dhi = lb.rhi[k] - q, dist, sg;
+          if (!((lb.limited >> k) & 1)) continue;
+          if (dlo < 0.f) { dist = dlo; sg = 1.f; }
+          else if (dhi < 0.f) { dist = dhi; sg = -1.f; }
+          else continue;
+          if (e >= lbs + lcnt) continue;
+          float* le = sm + C::lim + C::LIMW * e;
+          float imp = l_impedance(H, dist);
+          float4* l4 = (float4*)le;
+          l4[0] = make_float4(__int_as_float(d), sg, 1.0f / fmaxf((1.f - imp) / imp * lb.diw0[k], 1e-15f), -H.B * sg * sm[C::qvel + d] - H.K * imp * dist);
+          l4[1] = make_float4(0.f, __int_as_float(1), 0.f, 0.f);
+          e++;
         }
-        if (lcnt) {
-          int e = lbs;
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            int d = lb.dofadr + k;
-            float q = sm[C::qpos + d + 1], dlo = q - lb.rlo[k], dhi = lb.rhi[k] - q, dist, sg;
-            if (!((lb.limited >> k) & 1)) continue;
-            if (dlo < 0.f) { dist = dlo; sg = 1.f; }
-            else if (dhi < 0.f) { dist = dhi; sg = -1.f; }
-            else continue;
-            if (e >= lbs + lcnt) continue;
-            float* le = sm + C::lim + C::LIMW * e;
-            float imp = l_impedance(H, dist);
-            ((int*)le)[LLE_DOF] = d; le[LLE_SG] = sg;
-            le[LLE_D] = 1.0f / fmaxf((1.f - imp) / imp * lb.diw0[k], 1e-15f);
-            le[LLE_AREF] = -H.B * sg * sm[C::qvel + d] - H.K * imp * dist;
-            le[LLE_PHI] = 0.f; ((int*)le)[LLE_FLAG] = 1; le[LLE_R] = 0.f; le[LLE_RS] = 0.f;
-            e++;
-          }
-          npresent += lcnt;
-        }
+        npresent += lcnt;
       }
     }
+    if (flags & LF_VEL) l_rec_st_pb<C>(w, sm, t, b, pbv, actv);
     __syncwarp();
   }
   LFkOut o;
@@ -618,24 +744,61 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
 struct LSolveLane {       // lane-private sweep bookkeeping of one substep
   unsigned dirty_bits;    // bit t: the body of step t has constraint rows in its subtree
   unsigned rc_bits;       // bit t: the body of step t is recomputed by re-sweeps (dirty, or hands its result over in registers to such a body)
-  float dispx, dispy;     // root displacement of this substep (lane of the root body)
 };
 
-// root body of the inward sweep: (semi-implicit Euler of the free joint, then) elimination of its six dofs; the factors
-// K (6 x 6) and c (6) stay in shared memory
+// the active rows of the body's contacts folded into its articulated inertia / bias force: A += D x x^T, p -= D aref x
 template <class C>
-__device__ __noinline__ void l_root_in(const float* ms, float* sm, int flags, float* A, S6& p, LSolveLane& st) {
+__device__ __forceinline__ void l_fold_contacts(const LHdr& H, float* sm, const LLane& w, int cb, int cn, float* A, S6& p) {
+  for (int c = cb; c < cb + cn; c++) {
+    float e[12];
+    if (c < C::NCS) l_ld12(sm + C::con + C::CONW * c, e);
+    else { const float* ce = w.gscr + (size_t)C::CONW * (c - C::NCS); for (int j = 0; j < 12; j++) e[j] = ce[j]; }
+    const int info = __float_as_int(e[0]);
+    if (!(info & 1) || !(info & 30)) continue;
+    V3 cpt = v3(e[1], e[2], e[3]), t1 = v3(e[4], e[5], e[6]);
+    const float D = e[7];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (!(info & (2 << k))) continue;
+      S6 xw = l_wrench(H, cpt, t1, k);
+      float xv[6];
+      l_s6arr(xw, xv);
+      sym_rank1(A, xv, -D);
+      p = p - (D * e[8 + k]) * xw;
+    }
+  }
+}
+
+// root body of the inward sweep (every lane makes the call; lane 0 of the group works): children arrive through the
+// in-mailboxes; (semi-implicit Euler of the free joint, then) elimination of its six dofs; the factors K (6 x 6), c (6) stay in
+// shared memory.  Returns "the root has constraint rows in its subtree".
+template <class C>
+__device__ __noinline__ bool l_root_in(const float* ms, float* sm, const LLane& w, bool need, int flags) {
   const LHdr& H = l_hdr<C>(ms);
-  float* br = sm + C::body;
+  const LBody& lb = l_bodies(ms)[0];
+  S6 p = l_rec_ld_pb<C>(w, sm, 0, 0);
+  bool dirty = false;
+  if (need && w.li == 0) {
+    float* br = sm + C::body;
     float* rt = sm + C::root;
+    float A[21], r10[10];
+    const int ci = l_ld_r10(br, r10);
+    rb_expand(r10, A);
+    for (int j = 0; j < lb.nmb; j++) dirty = l_mbi_add(sm + C::mbi + C::MBIW * lb.mb[j], A, p) || dirty;
+    if (!(flags & LI_SPD)) {
+      const int cn = (ci >> 8) & 255;
+      dirty = dirty || cn > 0;
+      l_fold_contacts<C>(H, sm, w, ci & 255, cn, A, p);
+    }
     if (flags & LI_INTEGRATE) {
       float* qpos = sm + C::qpos; float* qvel = sm + C::qvel; const float* qacc = sm + C::qacc;
+      float* misc = sm + C::misc;
       float h = H.h;
 #pragma unroll
       for (int d = 0; d < 6; d++) {
         float v = fmaf(h, qacc[d], qvel[d]);
         qvel[d] = v;
-        if (d < 3) { float dd = h * v; qpos[d] += dd; if (d == 0) st.dispx += dd; if (d == 1) st.dispy += dd; }
+        if (d < 3) { float dd = h * v; qpos[d] += dd; if (d < 2) misc[LMI_DISP + d] += dd; }
       }
       V3 wv = ld3(qvel + 3);
       float n = sqrtf(dot(wv, wv)), ang = n * h;
@@ -668,12 +831,16 @@ __device__ __noinline__ void l_root_in(const float* ms, float* sm, int flags, fl
       for (int j = 0; j < 6; j++) rt[6 * k + j] = Uv[j] * di;
       rt[36 + k] = uu * di;
     }
+  }
+  __syncwarp();
+  return dirty;
 }
 
 template <class C>
-__device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane& w, bool run, int flags, LSolveLane& st) {
+__device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane& w, bool run, int flags, LSolveLane& st_) {
   const LHdr& H = l_hdr<C>(ms);
   const LBody* MB = l_bodies(ms);
+  LSolveLane st = st_;
   float cA[21];
 #pragma unroll
   for (int j = 0; j < 21; j++) cA[j] = 0.f;
@@ -681,7 +848,9 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
   bool cdirty = false;
   const bool spd = (flags & LI_SPD) != 0, resweep = (flags & LI_RESWEEP) != 0;
   if (!resweep && !spd) st.dirty_bits = 0u;
-  for (int t = H.T - 1; t >= 0; t--) {
+  const bool stepbar = (H.align & 16) && w.bar;
+  for (int t = H.T - 1; t >= 1; t--) {
+    if (stepbar) __syncthreads();
     const int b = H.sched[t][w.li];
     const bool actv = run && b >= 0;
     const bool need = actv && (!resweep || ((st.rc_bits >> t) & 1u));
@@ -694,169 +863,145 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
     if (need) {
       const LBody& lb = MB[b];
       float* br = sm + C::body + C::BODYW * b;
-      float A[21];
-      rb_expand(br + LBR_R10, A);
+      float A[21], r10[10];
+      const int ci = l_ld_r10(br, r10);
+      rb_expand(r10, A);
       bool dirty = false;
       if (lb.flags & LB_CARRY_IN) {
 #pragma unroll
         for (int j = 0; j < 21; j++) A[j] += cA[j];
         p = p + cp; dirty = cdirty;
       }
-      for (int j = 0; j < lb.nmb; j++) {
-        const float* mi = sm + C::mbi + C::MBIW * lb.mb[j];
-#pragma unroll
-        for (int i = 0; i < 21; i++) A[i] += mi[i];
-        p = p + ld6(mi + 21);
-        dirty = dirty || (((const int*)mi)[27] != 0);
-      }
+      for (int j = 0; j < lb.nmb; j++) dirty = l_mbi_add(sm + C::mbi + C::MBIW * lb.mb[j], A, p) || dirty;
       float lD[3] = {0.f, 0.f, 0.f}, lT[3] = {0.f, 0.f, 0.f};
       if (!spd) {
-        const int ci = ((const int*)br)[LBR_CI], cb = ci & 255, cn = (ci >> 8) & 255, lbs = (ci >> 16) & 255, ln = (ci >> 24) & 255;
+        const int cb = ci & 255, cn = (ci >> 8) & 255, lbs = (ci >> 16) & 255, ln = (ci >> 24) & 255;
         dirty = dirty || cn > 0 || ln > 0;
-        for (int c = cb; c < cb + cn; c++) {
-          const float* ce = l_centry<C>(sm, w, c);
-          int info = ((const int*)ce)[LCE_INFO];
-          if (!(info & 1) || !(info & 30)) continue;
-          V3 cpt = ld3(ce + LCE_CP), t1 = ld3(ce + LCE_T1);
-          float D = ce[LCE_D];
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            if (!(info & (2 << k))) continue;
-            S6 xw = l_wrench(H, cpt, t1, k);
-            float xv[6];
-            l_s6arr(xw, xv);
-            sym_rank1(A, xv, -D);
-            p = p - (D * ce[LCE_AREF + k]) * xw;
-          }
-        }
+        l_fold_contacts<C>(H, sm, w, cb, cn, A, p);
         for (int e = lbs; e < lbs + ln; e++) {   // joint-limit rows of this body that sit in the working set
-          const float* le = sm + C::lim + C::LIMW * e;
-          if (!(((const int*)le)[LLE_FLAG] & 1)) continue;
-          int k = ((const int*)le)[LLE_DOF] - lb.dofadr;
+          const float4* l4 = (const float4*)(sm + C::lim + C::LIMW * e);
+          float4 u = l4[0], v = l4[1];
+          if (!(__float_as_int(v.y) & 1)) continue;
+          int k = __float_as_int(u.x) - lb.dofadr;
 #pragma unroll
-          for (int kk = 0; kk < 3; kk++) if (kk == k) { lD[kk] = le[LLE_D]; lT[kk] = le[LLE_SG] * le[LLE_D] * le[LLE_AREF]; }
+          for (int kk = 0; kk < 3; kk++) if (kk == k) { lD[kk] = u.z; lT[kk] = u.y * u.z * u.w; }
         }
       }
-      if (t == 0) {   // the root body: out of line, once per sweep
-        l_root_in<C>(ms, sm, flags, A, p, st);
-      } else {
-        // ---------------- hinge body: three dofs, last joint first
-        const int d0 = lb.dofadr;
+      // ---------------- hinge body: three dofs, last joint first
+      const int d0 = lb.dofadr;
+      const LAxes AX = l_ld_axes(br);
 #pragma unroll
-        for (int k = 2; k >= 0; k--) {
-          const int d = d0 + k, i = d - 6;
-          S6 S = l_hingeS(br, k);
-          float s[6], Uv[6];
-          l_s6arr(S, s);
-          sym_mul(A, s, Uv);
-          float D = lb.arm[k] + (spd ? H.h * lb.kd[k] : lD[k]);
+      for (int k = 2; k >= 0; k--) {
+        const int d = d0 + k, i = d - 6;
+        V3 ax = l_axis(AX, k);
+        S6 S = s6(ax, cross(AX.x, ax));
+        float s[6], Uv[6];
+        l_s6arr(S, s);
+        sym_mul(A, s, Uv);
+        float D = lb.arm[k] + (spd ? H.h * lb.kd[k] : lD[k]);
 #pragma unroll
-          for (int j = 0; j < 6; j++) D = fmaf(s[j], Uv[j], D);
-          float di = l_rcp(D), tin;
-          if (spd) {
-            float q = sm[C::qpos + d + 1], qd = sm[C::qvel + d];
-            if (flags & LI_INTEGRATE) {
-              qd = fmaf(H.h, sm[C::qacc + d], qd); q = fmaf(H.h, qd, q);
-              sm[C::qvel + d] = qd; sm[C::qpos + d + 1] = q;
-            }
-            float tgt = fmaf(sm[C::act + i], lb.ascale[k], lb.aoffset[k]);
-            tin = -lb.kp[k] * (q + qd * H.h - tgt) - lb.kd[k] * qd;
-          } else tin = sm[C::tau + i] + lT[k];
-          float uu = tin - dot6(S, p);
-          sym_rank1(A, Uv, di);
-          p = p + (uu * di) * l_arr6(Uv);
+        for (int j = 0; j < 6; j++) D = fmaf(s[j], Uv[j], D);
+        float di = l_rcp(D), tin;
+        if (spd) {
+          float q = sm[C::qpos + d + 1], qd = sm[C::qvel + d];
+          if (flags & LI_INTEGRATE) {
+            qd = fmaf(H.h, sm[C::qacc + d], qd); q = fmaf(H.h, qd, q);
+            sm[C::qvel + d] = qd; sm[C::qpos + d + 1] = q;
+          }
+          float tgt = fmaf(sm[C::act + i], lb.ascale[k], lb.aoffset[k]);
+          tin = -lb.kp[k] * (q + qd * H.h - tgt) - lb.kd[k] * qd;
+        } else tin = sm[C::tau + i] + lT[k];
+        float uu = tin - dot6(S, p);
+        sym_rank1(A, Uv, di);
+        p = p + (uu * di) * l_arr6(Uv);
 #pragma unroll
-          for (int j = 0; j < 6; j++) K[6 * k + j] = Uv[j] * di;
-          kc[k] = uu * di;
-        }
+        for (int j = 0; j < 6; j++) K[6 * k + j] = Uv[j] * di;
+        kc[k] = uu * di;
       }
 #pragma unroll
       for (int j = 0; j < 21; j++) cA[j] = A[j];
       cp = p; cdirty = dirty;
-      if (lb.in_mbox >= 0) {
-        float* mi = sm + C::mbi + C::MBIW * lb.in_mbox;
-#pragma unroll
-        for (int j = 0; j < 21; j++) mi[j] = A[j];
-        st6(mi + 21, p);
-        ((int*)mi)[27] = dirty ? 1 : 0;
-      }
+      if (lb.in_mbox >= 0) l_mbi_put(sm + C::mbi + C::MBIW * lb.in_mbox, A, p, dirty);
       if (!spd && !resweep && dirty) st.dirty_bits |= 1u << t;
     }
-    if (t > 0) l_rec_st_Kc<C>(w, sm, t, b, K, kc, need, resweep);
+    l_rec_st_Kc<C>(w, sm, t, b, K, kc, need, resweep);
     __syncwarp();
   }
+  {   // the root body closes the sweep
+    if (stepbar) __syncthreads();
+    const bool need0 = run && (!resweep || (st.rc_bits & 1u));
+    bool d0 = false;
+    if (!resweep || __any_sync(L_FULL, need0)) d0 = l_root_in<C>(ms, sm, w, need0, flags);
+    if (!spd && !resweep && d0 && w.li == 0) st.dirty_bits |= 1u;
+  }
+  st_ = st;
 }
 
-// root body of the acceleration sweep: the six free-joint accelerations from the stored factors
+// root body of the acceleration sweep: the six free-joint accelerations from the stored factors (into the root's out-mailbox)
 template <class C>
-__device__ __noinline__ S6 l_root_acc(float* sm, float* qout) {
-  const float* rt = sm + C::root;
-  const float* br = sm + C::body;
-  S6 a = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
+__device__ __noinline__ void l_root_acc(const float* ms, float* sm, const LLane& w, bool run, float* qout, bool* same) {
+  const LHdr& H = l_hdr<C>(ms);
+  const LBody& lb = l_bodies(ms)[0];
+  if (run && w.li == 0) {
+    const float* rt = sm + C::root;
+    const float* br = sm + C::body;
+    S6 a = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
 #pragma unroll
-  for (int k = 0; k < 6; k++) {
-    S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
-                   : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
-    float qdd = rt[36 + k] - dot6(l_arr6(rt + 6 * k), a);
-    qout[k] = qdd;
-    a = a + qdd * S;
+    for (int k = 0; k < 6; k++) {
+      S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
+                     : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
+      float qdd = rt[36 + k] - dot6(l_arr6(rt + 6 * k), a);
+      qout[k] = qdd;
+      a = a + qdd * S;
+    }
+    l_mbo_put_acc(sm + C::mbo + C::MBOW * lb.out_mbox, a);
+    const int ci = ((const int*)br)[LBR_CI];
+    *same = l_rows_eval<C>(H, sm, w, ci & 255, (ci >> 8) & 255, a) && *same;
   }
-  return a;
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------ S3: outward sweep of the accelerations + residuals of the constraint rows
 // qdd -> qacc (no iterate yet) or qstar (trial point of the line search); rs = J a - aref of every row; returns "the sign pattern
 // of the rows equals the working set" for this lane's env.  first: also derive rc_bits from dirty_bits.
 template <class C>
-__device__ __noinline__ bool l_sweep_acc(const float* ms, float* sm, const LLane& w, bool run, bool to_qstar, bool first, LSolveLane& st) {
+__device__ __noinline__ bool l_sweep_acc(const float* ms, float* sm, const LLane& w, bool run, bool to_qstar, bool first, LSolveLane& st_) {
   const LHdr& H = l_hdr<C>(ms);
   const LBody* MB = l_bodies(ms);
+  LSolveLane st = st_;
   S6 ca = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
   bool crc = false, same = true;
   float* qout = sm + (to_qstar ? C::qstar : C::qacc);
-  if (first) st.rc_bits = 0u;
-  for (int t = 0; t < H.T; t++) {
+  if (first) st.rc_bits = (st.dirty_bits & 1u);   // the root (step 0, lane 0) is recomputed iff it is dirty
+  const bool stepbar = (H.align & 16) && w.bar;
+  if (stepbar) __syncthreads();
+  l_root_acc<C>(ms, sm, w, run, qout, &same);
+  for (int t = 1; t < H.T; t++) {
+    if (stepbar) __syncthreads();
     const int b = H.sched[t][w.li];
     const bool actv = run && b >= 0;
     float K[18], kc[3];
-    if (t > 0) l_rec_ld_Kc<C>(w, sm, t, b, K, kc);
+    l_rec_ld_Kc<C>(w, sm, t, b, K, kc);
     if (actv) {
       const LBody& lb = MB[b];
       const float* br = sm + C::body + C::BODYW * b;
-      S6 a;
-      float qdd3[3] = {0.f, 0.f, 0.f};
-      if (t == 0) {   // the root body: out of line
-        a = l_root_acc<C>(sm, qout);
-        crc = false;
-      } else {
-        if (!(lb.flags & LB_CARRY_OUT)) { ca = ld6(sm + C::mbo + C::MBOW * lb.pmbox + LMO_A); crc = false; }
-        a = ca;
+      if (!(lb.flags & LB_CARRY_OUT)) { ca = l_mbo_get_acc(sm + C::mbo + C::MBOW * lb.pmbox); crc = false; }
+      S6 a = ca;
+      float qdd3[3];
+      const LAxes AX = l_ld_axes(br);
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-          S6 S = l_hingeS(br, k);
-          float qdd = kc[k] - dot6(l_arr6(K + 6 * k), a);
-          qout[lb.dofadr + k] = qdd;
-          qdd3[k] = qdd;
-          a = a + qdd * S;
-        }
+      for (int k = 0; k < 3; k++) {
+        V3 ax = l_axis(AX, k);
+        S6 S = s6(ax, cross(AX.x, ax));
+        float qdd = kc[k] - dot6(l_arr6(K + 6 * k), a);
+        qdd3[k] = qdd;
+        a = a + qdd * S;
       }
+      qout[lb.dofadr] = qdd3[0]; qout[lb.dofadr + 1] = qdd3[1]; qout[lb.dofadr + 2] = qdd3[2];
       ca = a;
-      if (lb.out_mbox >= 0) st6(sm + C::mbo + C::MBOW * lb.out_mbox + LMO_A, a);
+      if (lb.out_mbox >= 0) l_mbo_put_acc(sm + C::mbo + C::MBOW * lb.out_mbox, a);
       const int ci = ((const int*)br)[LBR_CI], cb = ci & 255, cn = (ci >> 8) & 255, lbs = (ci >> 16) & 255, ln = (ci >> 24) & 255;
-      for (int c = cb; c < cb + cn; c++) {
-        float* ce = l_centry<C>(sm, w, c);
-        int info = ((const int*)ce)[LCE_INFO];
-        if (!(info & 1)) continue;
-        V3 cpt = ld3(ce + LCE_CP), t1 = ld3(ce + LCE_T1);
-        int nf = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          float rs = dot6(l_wrench(H, cpt, t1, k), a) - ce[LCE_AREF + k];
-          ce[LCE_RS + k] = rs;
-          if (rs < 0.f) nf |= 2 << k;
-        }
-        if (nf != (info & 30)) same = false;
-      }
+      if (cn) same = l_rows_eval<C>(H, sm, w, cb, cn, a) && same;
       for (int e = lbs; e < lbs + ln; e++) {
         float* le = sm + C::lim + C::LIMW * e;
         int k = ((const int*)le)[LLE_DOF] - lb.dofadr;
@@ -873,6 +1018,7 @@ __device__ __noinline__ bool l_sweep_acc(const float* ms, float* sm, const LLane
     }
     __syncwarp();
   }
+  st_ = st;
   return l_gall(same || !run, w);
 }
 
@@ -934,14 +1080,16 @@ __device__ __noinline__ int l_solve(const float* ms, float* sm, const LLane& w, 
   bool same0 = l_sweep_acc<C>(ms, sm, w, w.live, false, true, st);   // qdd -> qacc
   bool run = w.live && any_rows && !same0;
   *hit_max = false;
-  if (!__any_sync(L_FULL, run)) return 0;
+  // align bit 3: every warp of the CTA makes the same number of iterations (predicated), so all of them stay in the same sweep
+  const bool cu = (H.align & 8) && w.bar;
+  if (!(cu ? (__syncthreads_or(run) != 0) : __any_sync(L_FULL, run))) return 0;
   // envs whose first trial point changed the sign pattern: adopt it as the iterate, then iterate
   float o4[4];
   l_rows<C>(sm, w, run, 0, 0.f, o4);
   __syncwarp();
   int it = 1, iters = 0;
   for (; it < L_SOLVER_MAXITER; it++) {
-    if (!__any_sync(L_FULL, run)) break;
+    if (!(cu ? (__syncthreads_or(run) != 0) : __any_sync(L_FULL, run))) break;
     l_sweep_in<C>(ms, sm, w, run, H.dirtypath ? LI_RESWEEP : 0, st);
     bool same = l_sweep_acc<C>(ms, sm, w, run, true, false, st);      // qdd -> qstar
     bool fin = run && same, lsrch = run && !same;
@@ -1028,8 +1176,7 @@ __device__ __noinline__ void l_integrate(const float* ms, float* sm, const LLane
       for (int d = 0; d < 3; d++) {
         float v = fmaf(h, sm[C::qacc + d], sm[C::qvel + d]), dd = h * v;
         sm[C::qvel + d] = v; sm[C::qpos + d] += dd;
-        if (d == 0) st.dispx += dd;
-        if (d == 1) st.dispy += dd;
+        if (d < 2) sm[C::misc + LMI_DISP + d] += dd;
       }
     }
   }
@@ -1140,6 +1287,7 @@ __device__ __noinline__ void l_substeps(const float* ms, float* sm, const LLane&
     if (__any_sync(L_FULL, badacc != 0)) {   // mj_checkAcc: forward pass again on the reset data, then integrate
       LLane w2 = w;
       w2.live = w.live && badacc != 0;
+      w2.bar = false;
       LFkOut fk2 = l_sweep_out<C>(ms, sm, w2, LF_FK | LF_VEL | LF_COLLIDE | (last ? LF_SENS : 0), false);
       bool hit2 = false;
       int it2 = l_solve<C>(ms, sm, w2, fk2.nrows > 0, st, &hit2);
@@ -1372,6 +1520,7 @@ __device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int im
   w.gmask = ((1u << LM_LPE) - 1u) << (sub * LM_LPE);
   w.env = (blockIdx.x * wpb + wib) * C::EPW + sub;
   w.live = w.env < n;
+  w.bar = true;
   // tensor memory: a warp reaches the 32 lanes of its quarter (warp id mod 4); warps 4.. take the upper 256 columns
   w.tm = tbase + ((unsigned)((wib & 3) * 32) << 16) + (unsigned)((wib >> 2) * 256);
   w.gscr = gscr + (size_t)(w.live ? w.env : 0) * (size_t)(C::CONW * (C::NS - C::NCS));
@@ -1415,7 +1564,8 @@ __global__ void __launch_bounds__(256, 1) k_step5(const float* __restrict__ gimg
   const LHdr& H = l_hdr<C>(ms);
   const size_t eo = w.live ? (size_t)w.env : 0;   // lanes without a live env keep running (predicated): warp collectives stay legal
   const bool spd = (H.cfg.control_mode == SMPLSIM_CTRL_UHC_PD);
-  LSolveLane st; st.dirty_bits = 0u; st.rc_bits = 0u; st.dispx = 0.f; st.dispy = 0.f;
+  LSolveLane st; st.dirty_bits = 0u; st.rc_bits = 0u;
+  if (w.live && w.li == 0) { sm[C::misc + LMI_DISP] = 0.f; sm[C::misc + LMI_DISP + 1] = 0.f; }
   if (w.live) for (int i = w.li; i < (H.nslot + 3) / 4; i += LM_LPE) ((int*)sm)[C::pfl + i] = 0;   // no inherited working set at launch
   l_copy_in<C>(sm + C::act, a.action + eo * H.nu, H.nu, w);
   if (spd && H.cfg.spd_stale && a.mode == 0) l_spd_prologue<C>(ms, sm, w, a.st, st);
@@ -1439,7 +1589,7 @@ __global__ void __launch_bounds__(256, 1) k_step5(const float* __restrict__ gimg
     if (w.live && w.li == 0) ti[L_TSK_CURT] += 1;
     __syncwarp();
     l_write_obs<C>(ms, sm, w, a.obs ? a.obs + eo * H.obs_dim : nullptr);
-    float dx = __shfl_sync(L_FULL, st.dispx, w.gbase), dy = __shfl_sync(L_FULL, st.dispy, w.gbase);
+    const float dx = sm[C::misc + LMI_DISP], dy = sm[C::misc + LMI_DISP + 1];
     if (w.live && w.li == 0) {
       const SmplsimEnvCfg& c = H.cfg;
       const float* t = sm + C::tsk;
@@ -1477,7 +1627,8 @@ __global__ void __launch_bounds__(256, 1) k_reset5(const float* __restrict__ gim
   size_t eo = w.live ? (size_t)w.env : 0;
   const SmplsimEnvCfg& c = H.cfg;
   int init = a.init_mode < 0 ? c.state_init : a.init_mode;
-  LSolveLane st; st.dirty_bits = 0u; st.rc_bits = 0u; st.dispx = 0.f; st.dispy = 0.f;
+  LSolveLane st; st.dirty_bits = 0u; st.rc_bits = 0u;
+  if (w.live && w.li == 0) { sm[C::misc + LMI_DISP] = 0.f; sm[C::misc + LMI_DISP + 1] = 0.f; }
   l_task_io<C>(sm, w, a.st, false);
   if (w.live && w.li == 0) {
     int* ti = (int*)(sm + C::tsk);

@@ -232,6 +232,6 @@ static inline std::string lane_build(const SmplsimModelDesc* s, const SmplsimEnv
   for (int k = 0; k < 6; k++) H.rarm[k] = (float)s->dof_armature[k];
   H.cfg = *cfg;
   H.obs_dim = lane_obs_dims(s, cfg, &H.self_obs_dim);
-  H.warmset = 1; H.dirtypath = 1; H.ls_tol = 1e-6f; H.align = 0;
+  H.warmset = 1; H.dirtypath = 1; H.ls_tol = 1e-6f; H.align = 7;
   return "";
 }

@@ -41,11 +41,11 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
   for (unsigned b = 0; b < grid.x; b++) {
     c.bidx = dim3(b, 0, 0);
     memset(c.smem, 0xcd, smem);   // poison: reads of uninitialised shared memory show up as garbage, as on hardware
-    c.cta_arrived = 0; c.cta_gen = 0; c.cta_alive = nt;
+    c.cta_arrived = 0; c.cta_gen = 0; c.cta_alive = nt; c.or_acc[0] = c.or_acc[1] = 0;
     for (auto& w : c.warp) { w.arrived = 0; w.gen = 0; w.alive = 0; }
     for (int i = 0; i < nt; i++) {
       Thread& t = c.th[i];
-      t.tid = i; t.done = false; t.wait_kind = 0;
+      t.tid = i; t.done = false; t.wait_kind = 0; t.orcalls = 0;
       c.warp[i >> 5].alive++;
       getcontext(&t.ctx);
       t.ctx.uc_stack.ss_sp = t.stack; t.ctx.uc_stack.ss_size = kStack; t.ctx.uc_link = nullptr;

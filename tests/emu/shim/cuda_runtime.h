@@ -70,6 +70,7 @@ struct Thread {
   bool done;
   int wait_kind;   // 0 runnable, 1 waiting at a warp rendezvous, 2 waiting at the CTA barrier
   unsigned gen;
+  unsigned orcalls;
 };
 struct Warp {
   unsigned slot[32];
@@ -82,6 +83,7 @@ struct Cta {
   std::vector<Warp> warp;
   int nthreads, cta_arrived, cta_alive;
   unsigned cta_gen;
+  int or_acc[2];
   dim3 bidx, bdim, gdim;
   char* smem;
   uint32_t* tmem;   // [128][512]
@@ -139,6 +141,16 @@ static inline void emu_check_mask(unsigned m) {
 }
 static inline void __syncwarp(unsigned m = EMU_FULL) { emu_check_mask(m); emu::warp_arrive(); }
 static inline void __syncthreads() { emu::cta_barrier(); }
+static inline int __syncthreads_or(int p) {
+  emu::Cta& c = *emu::g_cta;
+  int k = (int)(emu::cur().orcalls++ & 1u);
+  c.or_acc[k] |= (p != 0);
+  emu::cta_barrier();
+  int r = c.or_acc[k];
+  c.or_acc[k ^ 1] = 0;
+  emu::cta_barrier();
+  return r;
+}
 static inline unsigned emu_bits(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float emu_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline unsigned emu_shfl(unsigned m, unsigned v, int src) {
