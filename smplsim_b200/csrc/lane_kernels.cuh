@@ -45,11 +45,11 @@ template <int NB_, int NV_, int NG_, int NS_, int NMBI_, int NMBO_, int NCS_, in
 struct LCfg {
   static constexpr int NB = NB_, NV = NV_, NQ = NV_ + 1, NU = NV_ - 6, NG = NG_, NS = NS_, NMBI = NMBI_, NMBO = NMBO_, NCS = NCS_, NLS = NLS_;
   static constexpr int RECT = RECT_, LPE = LM_LPE, EPW = 32 / LM_LPE;
-  static constexpr int BODYW = 24, MBIW = 28, MBOW = 28, CONW = 24, LIMW = 8, RECW = 28, ROOTW = 44;
+  static constexpr int BODYW = 24, MBIW = 28, MBOW = 32, CONW = 24, LIMW = 8, RECW = 28, ROOTW = 44;
   static constexpr int r4(int n) { return (n + 3) & ~3; }
   static constexpr int qpos = 0, qvel = qpos + r4(NQ), qacc = qvel + r4(NV), act = qacc + r4(NV), tau = act + r4(NU), qstar = tau + r4(NU),
                        body = qstar + r4(NV), mbi = body + BODYW * NB, mbo = mbi + MBIW * NMBI, root = mbo + MBOW * NMBO, con = root + ROOTW,
-                       lim = con + CONW * NCS, pfl = lim + LIMW * NLS, misc = pfl + r4((NS + 3) / 4), tsk = misc + 8,
+                       lim = con + CONW * NCS, pfl = lim + LIMW * NLS, PFLW = r4((NS + 3) / 4), misc = pfl + PFLW, tsk = misc + 8,
                        rec = tsk + 12, total_ = rec + (RECT ? 0 : RECW * NB);
   static constexpr int total = total_ | 4;   // env stride: a multiple of 4 words (float4 rows) but not of 8 (bank spread)
   // staging of the final kinematics / observation row: aliases the mailboxes, root factors and contact list (dead by then)
@@ -99,6 +99,7 @@ struct LLane {
   int env;
   unsigned tm;     // tensor-memory address of this warp's record block (RECT = 1)
   float* gscr;     // overflow contact entries of this env (global scratch)
+  int* gpfl;       // working set per contact slot carried across launches (handle-internal scratch, r4(NS / 4) words per env)
   float* gsens;    // framelinvel / frameangvel of the last forward pass [6 nb] of this env (global scratch; NULL: not wanted)
 };
 
@@ -149,6 +150,14 @@ __device__ __forceinline__ S6 l_wrench(const LHdr& H, V3 cp, V3 t1, int k) {
   float sg = (k & 1) ? -H.mu : H.mu;
   V3 dir = n + sg * t;
   return s6(cross(cp, dir), dir);
+}
+
+// direction of pyramid row k in the contact frame (n, t1, t2 = n x t1): n +- mu t1 | n +- mu t2.  The row's unit wrench about the
+// root origin is x_k = [cp x d_k ; d_k], so sums over rows factor through 3-vectors: sum D x x^T = X G X^T with G = D sum d d^T
+__device__ __forceinline__ V3 l_pyr_dir(const LHdr& H, V3 n, V3 t1, V3 t2, int k) {
+  V3 t = (k < 2) ? t1 : t2;
+  float sg = (k & 1) ? -H.mu : H.mu;
+  return n + sg * t;
 }
 
 // ------------------------------------------------------------------ lane records: [K 18 | c 3 | - | pb 6] per (lane, step)
@@ -315,7 +324,8 @@ __device__ __forceinline__ void l_rigid10(const LBody& lb, Q4 q, V3 x, float* r1
 #define LF_COLLIDE 8   // + floor contacts and joint-limit rows
 #define LF_SENS 16     // park framelinvel / frameangvel (quirk Q2: sensors of the last forward pass)
 #define LF_XQUAT 32    // store xquat rows (final kinematics)
-// out-mailbox of a junction body: [quat 4 | xpos 3 | - | v 6 | ab 6 | a 6]   (a: stable-PD acceleration in S1, trial acceleration in S3)
+// out-mailbox of a junction body: [quat 4 | xpos 3 | - | v 6 | ab 6 | pa 6 | a 6]   (pa: the previous substep's spatial
+// acceleration with the new joint axes; a: stable-PD acceleration in S1, trial acceleration in S3)
 #define LMO_Q 0
 #define LMO_X 4
 #define LMO_V 8
@@ -370,27 +380,29 @@ __device__ __forceinline__ void l_mbi_put(float* mi, const float* A, S6 p, bool 
   q[3] = make_float4(A[12], A[13], A[14], A[15]); q[4] = make_float4(A[16], A[17], A[18], A[19]);
   q[5] = make_float4(A[20], p.a.x, p.a.y, p.a.z); q[6] = make_float4(p.l.x, p.l.y, p.l.z, __int_as_float(dirty ? 1 : 0));
 }
-// out-mailbox pose part [quat 4 | xpos 3 | - | v 6 | ab 6] (words 0..19) and acceleration part (words 20..25)
-struct LPose { Q4 q; V3 x; S6 v, ab; };
+// out-mailbox pose part [quat 4 | xpos 3 | - | v 6 | ab 6 | pa 6] (words 0..25) and acceleration part (words 26..31)
+struct LPose { Q4 q; V3 x; S6 v, ab, pa; };
 __device__ __forceinline__ void l_mbo_put_pose(float* mo, const LPose& P) {
   float4* q = (float4*)mo;
   q[0] = make_float4(P.q.w, P.q.x, P.q.y, P.q.z); q[1] = make_float4(P.x.x, P.x.y, P.x.z, 0.f);
   q[2] = make_float4(P.v.a.x, P.v.a.y, P.v.a.z, P.v.l.x); q[3] = make_float4(P.v.l.y, P.v.l.z, P.ab.a.x, P.ab.a.y);
-  q[4] = make_float4(P.ab.a.z, P.ab.l.x, P.ab.l.y, P.ab.l.z);
+  q[4] = make_float4(P.ab.a.z, P.ab.l.x, P.ab.l.y, P.ab.l.z); q[5] = make_float4(P.pa.a.x, P.pa.a.y, P.pa.a.z, P.pa.l.x);
+  mo[24] = P.pa.l.y; mo[25] = P.pa.l.z;
 }
 __device__ __forceinline__ void l_mbo_get_pose(const float* mo, LPose& P) {
   const float4* q = (const float4*)mo;
-  float4 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4];
+  float4 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4], f = q[5];
   P.q.w = a.x; P.q.x = a.y; P.q.y = a.z; P.q.z = a.w; P.x = v3(b.x, b.y, b.z);
   P.v = s6(v3(c.x, c.y, c.z), v3(c.w, d.x, d.y)); P.ab = s6(v3(d.z, d.w, e.x), v3(e.y, e.z, e.w));
+  P.pa = s6(v3(f.x, f.y, f.z), v3(f.w, mo[24], mo[25]));
 }
 __device__ __forceinline__ void l_mbo_put_acc(float* mo, S6 a) {
-  ((float4*)mo)[5] = make_float4(a.a.x, a.a.y, a.a.z, a.l.x);
-  mo[24] = a.l.y; mo[25] = a.l.z;
+  mo[26] = a.a.x; mo[27] = a.a.y;
+  ((float4*)mo)[7] = make_float4(a.a.z, a.l.x, a.l.y, a.l.z);
 }
 __device__ __forceinline__ S6 l_mbo_get_acc(const float* mo) {
-  float4 a = ((const float4*)mo)[5];
-  return s6(v3(a.x, a.y, a.z), v3(a.w, mo[24], mo[25]));
+  float4 a = ((const float4*)mo)[7];
+  return s6(v3(mo[26], mo[27], a.x), v3(a.y, a.z, a.w));
 }
 // joint axes + body position of a body row (words 0..11)
 struct LAxes { V3 a0, a1, a2, x; };
@@ -414,11 +426,13 @@ __device__ __forceinline__ bool l_rows_eval(const LHdr& H, float* sm, const LLan
     const int info = __float_as_int(e[0]);
     if (!(info & 1)) continue;
     V3 cpt = v3(e[1], e[2], e[3]), t1 = v3(e[4], e[5], e[6]);
+    const V3 n = ld3(H.plane_n), t2 = cross(n, t1);
+    const V3 ac = a.l + cross(a.a, cpt);    // X^T a: acceleration of the contact point
     int nf = 0;
     float rs[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      rs[k] = dot6(l_wrench(H, cpt, t1, k), a) - e[8 + k];
+      rs[k] = dot(l_pyr_dir(H, n, t1, t2, k), ac) - e[8 + k];
       if (rs[k] < 0.f) nf |= 2 << k;
     }
     if (c < C::NCS) ((float4*)(sm + C::con + C::CONW * c))[LCE_RS / 4] = make_float4(rs[0], rs[1], rs[2], rs[3]);
@@ -470,7 +484,7 @@ __device__ __forceinline__ int l_broad(const LHdr& H, const LGeom& G, const LPos
 // narrow phase (plane vs box corners / capsule ends / sphere) into the reserved entries [cb, cb + alloc); returns
 // the number of contacts
 template <class C>
-__device__ __forceinline__ int l_narrow(const LHdr& H, const LGeom& G, int g, const LGeomCtx& X, S6 vb, float tiw0, float* sm, const LLane& w, int cb, int alloc) {
+__device__ __forceinline__ int l_narrow(const LHdr& H, const LGeom& G, int g, const LGeomCtx& X, S6 vb, S6 pa, float tiw0, float* sm, const LLane& w, int cb, int alloc) {
   const V3 pn = ld3(H.plane_n);
   const unsigned char* pf = (const unsigned char*)(sm + C::pfl);
   V3 t1 = ld3(H.t1_default);
@@ -501,14 +515,26 @@ __device__ __forceinline__ int l_narrow(const LHdr& H, const LGeom& G, int g, co
     float R0 = fmaxf((1.f - imp) / imp * (tiw0 + H.mu * H.mu * tiw0), 1e-15f);
     float R1 = R0 / fmaxf(H.impratio, 1e-15f), mu = H.mu * sqrtf(R1 / R0);
     float kterm = H.K * imp * pm;
-    // working set inherited from the slot's previous substep; new contacts start with all four rows active
-    int slot = G.slot0 + cnt, pv = pf[slot];
+    // working set inherited from the slot's previous substep; a new contact starts from the rows that would be violated if the
+    // body kept the acceleration it had in the previous substep
+    int slot = G.slot0 + cnt, pv = pf[slot], guess = 32;   // bit 5: new this substep
     float e[12];
-    e[0] = __int_as_float(1 | ((pv & 1) ? (pv & 30) : 30) | (g << 8) | (slot << 16));
     e[1] = cp.x; e[2] = cp.y; e[3] = cp.z; e[4] = t1.x; e[5] = t1.y; e[6] = t1.z;
     e[7] = 1.0f / (2.f * mu * mu * R0);
+    {
+      const V3 t2 = cross(pn, t1);
+      const V3 vc = vb.l + cross(vb.a, cp), pc = pa.l + cross(pa.a, cp);   // velocity / previous acceleration of the contact point
 #pragma unroll
-    for (int k = 0; k < 4; k++) e[8 + k] = -H.B * dot6(l_wrench(H, cp, t1, k), vb) - kterm;
+      for (int k = 0; k < 4; k++) {
+        V3 d = l_pyr_dir(H, pn, t1, t2, k);
+        e[8 + k] = -H.B * dot(d, vc) - kterm;
+        if (dot(d, pc) - e[8 + k] < 0.f) guess |= 2 << k;
+      }
+    }
+    e[0] = __int_as_float(1 | ((pv & 1) ? (pv & 30) : guess) | (g << 8) | (slot << 16));
+#ifdef SMPLSIM_STATS
+    e[0] = __int_as_float(__float_as_int(e[0]) | ((((pv & 1) ? (pv & 30) : 30) >> 1) << 24) | (((guess & 30) >> 1) << 28));
+#endif
     const int c = cb + cnt;
     if (c < C::NCS) l_st12(sm + C::con + C::CONW * c, e);
     else { float* ce = w.gscr + (size_t)C::CONW * (c - C::NCS); for (int j = 0; j < 12; j++) ce[j] = e[j]; }
@@ -562,18 +588,20 @@ __device__ __noinline__ LRootOut l_root_out(const float* ms, float* sm, const LL
       st3(br + LBR_AX, c0); st3(br + LBR_AX + 3, c1); st3(br + LBR_AX + 6, c2);
       P.x = v3(0.f, 0.f, 0.f);
       st3(br + LBR_X, P.x);
-      P.v = s6(P.x, P.x); P.ab = P.v;
+      P.v = s6(P.x, P.x); P.ab = P.v; P.pa = P.v;
       if (flags & LF_VEL) {
         V3 vl = ld3(qvel), wv = qvel[3] * c0 + qvel[4] * c1 + qvel[5] * c2;
         P.v = s6(wv, vl);
         P.ab = s6(v3(0.f, 0.f, 0.f), v3(-H.grav[0], -H.grav[1], -H.grav[2]) + cross(vl, wv));
+        const float* qa = sm + C::qacc;   // acceleration of the previous substep (qacc_warmstart), new rotation columns
+        P.pa = s6(qa[3] * c0 + qa[4] * c1 + qa[5] * c2, ld3(qa));
       }
       l_mbo_put_pose(mo, P);
       LGeomCtx X;
       if ((flags & LF_COLLIDE) && lb.ngeom > 0) alloc = l_broad(H, l_geoms(ms)[lb.geom0], P, h0, X);
       pbv = l_body_post<C>(lb, sm, w, 0, flags, P, br, alloc << 8);
       if (alloc) {
-        int cnt = l_narrow<C>(H, l_geoms(ms)[lb.geom0], lb.geom0, X, P.v, lb.tiw0, sm, w, 0, alloc);
+        int cnt = l_narrow<C>(H, l_geoms(ms)[lb.geom0], lb.geom0, X, P.v, P.pa, lb.tiw0, sm, w, 0, alloc);
         if (cnt) R.gbits = 1ull << (lb.geom0 + 1);
         R.npresent = cnt;
       }
@@ -593,7 +621,7 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
   const float h0 = dot(ld3(H.plane_n), ld3(sm + C::qpos) - ld3(H.plane_pos));
   LRootOut R0 = l_root_out<C>(ms, sm, w, flags, h0);
   LPose P;   // pose / velocity / bias acceleration handed down the lane's chain
-  P.q.w = 1.f; P.q.x = P.q.y = P.q.z = 0.f; P.x = v3(0.f, 0.f, 0.f); P.v = s6(P.x, P.x); P.ab = P.v;
+  P.q.w = 1.f; P.q.x = P.q.y = P.q.z = 0.f; P.x = v3(0.f, 0.f, 0.f); P.v = s6(P.x, P.x); P.ab = P.v; P.pa = P.v;
   S6 casp = P.v;
   int ncon = R0.ncon, nlim = 0, npresent = R0.npresent, dropped = 0;
   unsigned long long gbits = R0.gbits;
@@ -647,7 +675,7 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
         V3 x = P.x + mrot(Rp, ld3(lb.bpos));
         Q4 qb; qb.w = lb.bquat[0]; qb.x = lb.bquat[1]; qb.y = lb.bquat[2]; qb.z = lb.bquat[3];
         Q4 qc = qmul(P.q, qb);
-        S6 v = P.v, ab = P.ab;
+        S6 v = P.v, ab = P.ab, pa = P.pa;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
           V3 al = ld3(lb.axis + 3 * k);
@@ -658,6 +686,7 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
             float qd = k == 0 ? qd0 : k == 1 ? qd1 : qd2;
             ab = ab + qd * cross_motion(v, S);
             v = v + qd * S;
+            if (flags & LF_COLLIDE) pa = pa + sm[C::qacc + d0 + k] * S;   // previous acceleration: working-set guess of new contacts
           }
           float sn, cs;
           l_sincos(0.5f * (k == 0 ? q0 : k == 1 ? q1 : q2), &sn, &cs);
@@ -667,7 +696,7 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
         qc = qnormalize(qc);
         row[9] = x.x; row[10] = x.y; row[11] = x.z;
         l_st12(br, row);
-        P.q = qc; P.x = x; P.v = v; P.ab = ab;
+        P.q = qc; P.x = x; P.v = v; P.ab = ab; P.pa = pa;
         if (lb.out_mbox >= 0) l_mbo_put_pose(sm + C::mbo + C::MBOW * lb.out_mbox, P);
         if (flags & LF_COLLIDE) {
           if (lb.ngeom > 0) alloc = l_broad(H, MG[lb.geom0], P, h0, X);
@@ -692,7 +721,7 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
       const LBody& lb = MB[b];
       pbv = l_body_post<C>(lb, sm, w, b, flags, P, br, cb | (alloc << 8) | (lbs << 16) | (lcnt << 24));
       if (alloc) {
-        int cnt = l_narrow<C>(H, MG[lb.geom0], lb.geom0, X, P.v, lb.tiw0, sm, w, cb, alloc);
+        int cnt = l_narrow<C>(H, MG[lb.geom0], lb.geom0, X, P.v, P.pa, lb.tiw0, sm, w, cb, alloc);
         if (cnt) gbits |= 1ull << (lb.geom0 + 1);
         npresent += cnt;
       }
@@ -756,16 +785,32 @@ __device__ __forceinline__ void l_fold_contacts(const LHdr& H, float* sm, const 
     const int info = __float_as_int(e[0]);
     if (!(info & 1) || !(info & 30)) continue;
     V3 cpt = v3(e[1], e[2], e[3]), t1 = v3(e[4], e[5], e[6]);
+    const V3 n = ld3(H.plane_n), t2 = cross(n, t1);
     const float D = e[7];
+    // G = D sum_active d d^T (xx yy zz xy xz yz), f = D sum_active aref d
+    float gxx = 0.f, gyy = 0.f, gzz = 0.f, gxy = 0.f, gxz = 0.f, gyz = 0.f;
+    V3 f = v3(0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       if (!(info & (2 << k))) continue;
-      S6 xw = l_wrench(H, cpt, t1, k);
-      float xv[6];
-      l_s6arr(xw, xv);
-      sym_rank1(A, xv, -D);
-      p = p - (D * e[8 + k]) * xw;
+      V3 d = l_pyr_dir(H, n, t1, t2, k);
+      V3 dd = D * d;
+      gxx = fmaf(dd.x, d.x, gxx); gyy = fmaf(dd.y, d.y, gyy); gzz = fmaf(dd.z, d.z, gzz);
+      gxy = fmaf(dd.x, d.y, gxy); gxz = fmaf(dd.x, d.z, gxz); gyz = fmaf(dd.y, d.z, gyz);
+      f = f + e[8 + k] * dd;
     }
+    // A += X G X^T with X = [[cp]x ; I]:  A_ll += G ; A_al += [cp]x G ; A_aa += [cp]x G [cp]x^T
+    const V3 g0 = v3(gxx, gxy, gxz), g1 = v3(gxy, gyy, gyz), g2 = v3(gxz, gyz, gzz);   // columns (= rows) of G
+    const V3 c0 = cross(cpt, g0), c1 = cross(cpt, g1), c2 = cross(cpt, g2);           // columns of M = [cp]x G  (3 x 3)
+    A[sidx(3, 3)] += gxx; A[sidx(4, 4)] += gyy; A[sidx(5, 5)] += gzz; A[sidx(3, 4)] += gxy; A[sidx(3, 5)] += gxz; A[sidx(4, 5)] += gyz;
+    A[sidx(0, 3)] += c0.x; A[sidx(1, 3)] += c0.y; A[sidx(2, 3)] += c0.z;
+    A[sidx(0, 4)] += c1.x; A[sidx(1, 4)] += c1.y; A[sidx(2, 4)] += c1.z;
+    A[sidx(0, 5)] += c2.x; A[sidx(1, 5)] += c2.y; A[sidx(2, 5)] += c2.z;
+    // A_aa += M [cp]x^T : row i of M is (c0.i, c1.i, c2.i); (M [cp]x^T)_ij = (cp x row_i)_j ... symmetric, upper triangle
+    const V3 r0 = v3(c0.x, c1.x, c2.x), r1 = v3(c0.y, c1.y, c2.y), r2 = v3(c0.z, c1.z, c2.z);
+    const V3 m0 = cross(cpt, r0), m1 = cross(cpt, r1), m2 = cross(cpt, r2);
+    A[sidx(0, 0)] += m0.x; A[sidx(0, 1)] += m0.y; A[sidx(0, 2)] += m0.z; A[sidx(1, 1)] += m1.y; A[sidx(1, 2)] += m1.z; A[sidx(2, 2)] += m2.z;
+    p.l = p.l - f; p.a = p.a - cross(cpt, f);
   }
 }
 
@@ -813,18 +858,24 @@ __device__ __noinline__ bool l_root_in(const float* ms, float* sm, const LLane& 
       q = qnormalize(q);
       qpos[3] = q.w; qpos[4] = q.x; qpos[5] = q.y; qpos[6] = q.z;
     }
+    // free joint: S_k = (0, e_k) for the translations, (column k-3 of R, 0) for the rotations -> U is a column of A or a
+    // product with its angular block only
 #pragma unroll
     for (int k = 5; k >= 0; k--) {
-      S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
-                     : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
-      float s[6], Uv[6];
-      l_s6arr(S, s);
-      sym_mul(A, s, Uv);
-      float D = H.rarm[k];
+      float Uv[6], D = H.rarm[k], uu;
+      if (k < 3) {
 #pragma unroll
-      for (int j = 0; j < 6; j++) D = fmaf(s[j], Uv[j], D);
+        for (int i = 0; i < 6; i++) Uv[i] = A[sidx(i, 3 + k)];
+        D += Uv[3 + k];
+        uu = -(k == 0 ? p.l.x : k == 1 ? p.l.y : p.l.z);
+      } else {
+        const V3 c = ld3(br + LBR_AX + 3 * (k - 3));
+#pragma unroll
+        for (int i = 0; i < 6; i++) Uv[i] = fmaf(A[sidx(i, 0)], c.x, fmaf(A[sidx(i, 1)], c.y, A[sidx(i, 2)] * c.z));
+        D += fmaf(c.x, Uv[0], fmaf(c.y, Uv[1], c.z * Uv[2]));
+        uu = -dot(c, p.a);
+      }
       float di = l_rcp(D);
-      float uu = -dot6(S, p);
       sym_rank1(A, Uv, di);
       p = p + (uu * di) * l_arr6(Uv);
 #pragma unroll
@@ -1070,6 +1121,16 @@ __device__ __noinline__ void l_rows(float* sm, const LLane& w, bool run, int op,
   out4[0] = g1; out4[1] = g2; out4[2] = s1; out4[3] = s2;
 }
 
+#ifdef SMPLSIM_STATS
+// debug build (tools/solver_stats.py): why does the first solve of a substep miss?  counters: [0] env-substeps, [1] with rows,
+// [2] first pass ok, [3..8] histogram of extra solves 1..6+, [9] rows predicted active but rs >= 0, [10] rows predicted inactive
+// but rs < 0, [11] ... of which in a contact new this substep, [12] limit rows flipped, [13] contacts, [14] new contacts
+__device__ int g_lstats[32];
+#define L_STAT(i, v) atomicAdd(&g_lstats[i], v)
+#else
+#define L_STAT(i, v) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------ constraint solve: active-set Newton, every system one ABA pass
 // Returns the number of extra solves; *hit_max: stopped at L_SOLVER_MAXITER.
 template <class C>
@@ -1080,6 +1141,32 @@ __device__ __noinline__ int l_solve(const float* ms, float* sm, const LLane& w, 
   bool same0 = l_sweep_acc<C>(ms, sm, w, w.live, false, true, st);   // qdd -> qacc
   bool run = w.live && any_rows && !same0;
   *hit_max = false;
+#ifdef SMPLSIM_STATS
+  if (w.live && w.li == 0) {
+    L_STAT(0, 1);
+    if (any_rows) L_STAT(1, 1);
+    if (any_rows && same0) L_STAT(2, 1);
+    const int ncon = ((const int*)sm)[C::misc + LMI_NCON], nlim = ((const int*)sm)[C::misc + LMI_NLIM];
+    for (int c = 0; c < ncon; c++) {
+      const float* ce = l_centry<C>(sm, w, c);
+      int info = ((const int*)ce)[LCE_INFO];
+      if (!(info & 1)) continue;
+      L_STAT(13, 1);
+      bool isnew = ((info >> 5) & 1) != 0;
+      if (isnew) L_STAT(14, 1);
+      for (int k = 0; k < 4; k++) {
+        bool act = (info & (2 << k)) != 0, neg = ce[LCE_RS + k] < 0.f;
+        if (act && !neg) L_STAT(9, 1);
+        if (!act && neg) L_STAT(10, 1);
+        if (act != neg && isnew) L_STAT(11, 1);
+      }
+    }
+    for (int e = 0; e < nlim; e++) {
+      const float* le = sm + C::lim + C::LIMW * e;
+      if ((le[LLE_RS] < 0.f ? 1 : 0) != (((const int*)le)[LLE_FLAG] & 1)) L_STAT(12, 1);
+    }
+  }
+#endif
   // align bit 3: every warp of the CTA makes the same number of iterations (predicated), so all of them stay in the same sweep
   const bool cu = (H.align & 8) && w.bar;
   if (!(cu ? (__syncthreads_or(run) != 0) : __any_sync(L_FULL, run))) return 0;
@@ -1127,6 +1214,20 @@ __device__ __noinline__ int l_solve(const float* ms, float* sm, const LLane& w, 
     __syncwarp();
   }
   if (run) { iters = it; *hit_max = true; }
+#ifdef SMPLSIM_STATS
+  if (w.live && w.li == 0 && iters > 0) L_STAT(2 + (iters > 6 ? 6 : iters), 1);
+  if (w.live && w.li == 0) {   // [16] rows, [17] inherit guess wrong vs the final set, [18] prediction wrong, [19] both wrong, [20] contacts where inherit is right, [21] pred right
+    const int ncon = ((const int*)sm)[C::misc + LMI_NCON];
+    for (int c = 0; c < ncon; c++) {
+      int info = ((const int*)l_centry<C>(sm, w, c))[LCE_INFO];
+      if (!(info & 1)) continue;
+      int fin = (info >> 1) & 15, inh = (info >> 24) & 15, prd = (info >> 28) & 15;
+      L_STAT(16, 4); L_STAT(17, __popc(fin ^ inh)); L_STAT(18, __popc(fin ^ prd)); L_STAT(19, __popc((fin ^ inh) & (fin ^ prd)));
+      if (fin == inh) L_STAT(20, 1);
+      if (fin == prd) L_STAT(21, 1);
+    }
+  }
+#endif
   return iters;
 }
 
@@ -1251,6 +1352,8 @@ __device__ __forceinline__ void l_save_working_set(const float* ms, float* sm, c
 
 struct LFwd { unsigned long long mask; int iters; int status; };
 
+
+
 // ------------------------------------------------------------------ nsub x [compute_torque + mj_step]   (humanoid_env.py:439-453)
 // Entry condition in stable-PD (stale) mode: records hold the (M + h Kd) factors of the last forward pass for the state in
 // qpos / qvel and the action in act (prologue of the kernels: l_spd_prologue).
@@ -1322,6 +1425,7 @@ struct LStepArgs {
   uint8_t* truncated;
   float* gscr;       // [n, (NS - NCS) * CONW] overflow contact entries
   float* gsens;      // [n, 6 nb] or NULL
+  int* gpfl;         // [n, r4(NS / 4)] working set per contact slot
   int n, nsub, mode;
 };
 struct LResetArgs {
@@ -1333,6 +1437,7 @@ struct LResetArgs {
   float* obs;
   float* gscr;
   float* gsens;
+  int* gpfl;
   int n, init_mode;
 };
 struct LKinArgs { const float* qpos; float* xpos; float* xquat; int n; };
@@ -1487,7 +1592,7 @@ extern __shared__ float4 l_smem4[];
 
 // CTA prologue: stage the constant table, carve the env rows, claim tensor memory.  Shared memory: [table | 4 words | env rows]
 template <class C>
-__device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int img_bytes, LLane& w, const float*& ms, int n, float* gscr, float* gsens) {
+__device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int img_bytes, LLane& w, const float*& ms, int n, float* gscr, float* gsens, int* gpfl) {
   float* smem = L_SMEM;
   {
     const uint4* src = (const uint4*)gimg;
@@ -1524,6 +1629,7 @@ __device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int im
   // tensor memory: a warp reaches the 32 lanes of its quarter (warp id mod 4); warps 4.. take the upper 256 columns
   w.tm = tbase + ((unsigned)((wib & 3) * 32) << 16) + (unsigned)((wib >> 2) * 256);
   w.gscr = gscr + (size_t)(w.live ? w.env : 0) * (size_t)(C::CONW * (C::NS - C::NCS));
+  w.gpfl = gpfl ? gpfl + (size_t)(w.live ? w.env : 0) * (size_t)C::PFLW : nullptr;
   w.gsens = gsens ? gsens + (size_t)(w.live ? w.env : 0) * (size_t)(6 * C::NB) : nullptr;
   return smem + img_bytes / 4 + 4 + (size_t)(wib * C::EPW + sub) * C::total;
 }
@@ -1560,13 +1666,13 @@ __device__ __noinline__ void l_spd_prologue(const float* ms, float* sm, const LL
 template <class C>
 __global__ void __launch_bounds__(256, 1) k_step5(const float* __restrict__ gimg, int img_bytes, LStepArgs a) {
   const float* ms; LLane w;
-  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.gscr, a.gsens);
+  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.gscr, a.gsens, a.gpfl);
   const LHdr& H = l_hdr<C>(ms);
   const size_t eo = w.live ? (size_t)w.env : 0;   // lanes without a live env keep running (predicated): warp collectives stay legal
   const bool spd = (H.cfg.control_mode == SMPLSIM_CTRL_UHC_PD);
   LSolveLane st; st.dirty_bits = 0u; st.rc_bits = 0u;
   if (w.live && w.li == 0) { sm[C::misc + LMI_DISP] = 0.f; sm[C::misc + LMI_DISP + 1] = 0.f; }
-  if (w.live) for (int i = w.li; i < (H.nslot + 3) / 4; i += LM_LPE) ((int*)sm)[C::pfl + i] = 0;   // no inherited working set at launch
+  if (w.live) for (int i = w.li; i < (H.nslot + 3) / 4; i += LM_LPE) ((int*)sm)[C::pfl + i] = w.gpfl ? w.gpfl[i] : 0;   // working set of the previous call
   l_copy_in<C>(sm + C::act, a.action + eo * H.nu, H.nu, w);
   if (spd && H.cfg.spd_stale && a.mode == 0) l_spd_prologue<C>(ms, sm, w, a.st, st);
   else {
@@ -1614,6 +1720,7 @@ __global__ void __launch_bounds__(256, 1) k_step5(const float* __restrict__ gimg
   l_copy_out<C>(a.st.qpos + eo * (H.nv + 1), sm + C::qpos, H.nv + 1, w);
   l_copy_out<C>(a.st.qvel + eo * H.nv, sm + C::qvel, H.nv, w);
   l_copy_out<C>(a.st.qacc_warm + eo * H.nv, sm + C::qacc, H.nv, w);
+  if (w.live && w.gpfl) for (int i = w.li; i < (H.nslot + 3) / 4; i += LM_LPE) w.gpfl[i] = ((const int*)sm)[C::pfl + i];
   if (a.mode == 0) l_task_io<C>(sm, w, a.st, true);
   l_teardown<C>(ms);
 }
@@ -1621,7 +1728,7 @@ __global__ void __launch_bounds__(256, 1) k_step5(const float* __restrict__ gimg
 template <class C>
 __global__ void __launch_bounds__(256, 1) k_reset5(const float* __restrict__ gimg, int img_bytes, LResetArgs a) {
   const float* ms; LLane w;
-  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.gscr, a.gsens);
+  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.gscr, a.gsens, a.gpfl);
   const LHdr& H = l_hdr<C>(ms);
   if (w.live && a.mask && !a.mask[w.env]) w.live = false;
   size_t eo = w.live ? (size_t)w.env : 0;
@@ -1689,6 +1796,7 @@ __global__ void __launch_bounds__(256, 1) k_reset5(const float* __restrict__ gim
   l_copy_out<C>(a.st.qpos_fwd + eo * (H.nv + 1), sm + C::qpos, H.nv + 1, w);
   l_copy_out<C>(a.st.qvel_fwd + eo * H.nv, sm + C::qvel, H.nv, w);
   l_copy_out<C>(a.st.qacc_warm + eo * H.nv, sm + C::qacc, H.nv, w);
+  if (w.live && w.gpfl) for (int i = w.li; i < (H.nslot + 3) / 4; i += LM_LPE) w.gpfl[i] = ((const int*)sm)[C::pfl + i];
   l_task_io<C>(sm, w, a.st, true);
   l_teardown<C>(ms);
 }
@@ -1697,7 +1805,7 @@ __global__ void __launch_bounds__(256, 1) k_reset5(const float* __restrict__ gim
 template <class C>
 __global__ void __launch_bounds__(256, 1) k_kin5(const float* __restrict__ gimg, int img_bytes, LKinArgs a) {
   const float* ms; LLane w;
-  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, nullptr, nullptr);
+  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, nullptr, nullptr, nullptr);
   const LHdr& H = l_hdr<C>(ms);
   size_t eo = w.live ? (size_t)w.env : 0;
   l_copy<C>(sm + C::qpos, a.qpos + eo * (H.nv + 1), H.nv + 1, w);

@@ -27,6 +27,7 @@ struct SmplsimHandle {
   float* dimg = nullptr;   // device copy of the table
   float* gscr = nullptr;   // overflow contact entries
   float* gsens = nullptr;  // body velocities of the last forward pass (obs v2 / aux)
+  int* gpfl = nullptr;     // working set per contact slot, carried from call to call (solver warm start only)
   int num_envs = 0, device = 0, nsm = 148, max_smem = 0;
   int cls = 0;             // 1 SMPL class, 2 SMPL-X class
   int rect = 1;            // lane records in tensor memory (1) or shared memory (0)
@@ -146,7 +147,11 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   if (e == cudaSuccess) e = cudaMemcpy(h->dimg, h->img.bytes.data(), H.bytes, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&h->gscr, gs * (size_t)num_envs * 4 + 16);
   if (e == cudaSuccess) e = cudaMalloc(&h->gsens, (size_t)6 * H.nb * num_envs * 4);
-  if (e != cudaSuccess) { if (h->dimg) cudaFree(h->dimg); if (h->gscr) cudaFree(h->gscr); if (h->gsens) cudaFree(h->gsens); delete h; return fail(SMPLSIM_ECUDA, std::string("smplsim_create: ") + cudaGetErrorString(e)); }
+  size_t pw = 0;
+  L_DISPATCH(h, pw = (size_t)C_::PFLW);
+  if (e == cudaSuccess) e = cudaMalloc(&h->gpfl, pw * num_envs * 4);
+  if (e == cudaSuccess) e = cudaMemset(h->gpfl, 0, pw * num_envs * 4);
+  if (e != cudaSuccess) { if (h->dimg) cudaFree(h->dimg); if (h->gscr) cudaFree(h->gscr); if (h->gsens) cudaFree(h->gsens); if (h->gpfl) cudaFree(h->gpfl); delete h; return fail(SMPLSIM_ECUDA, std::string("smplsim_create: ") + cudaGetErrorString(e)); }
   *out = h;
   return SMPLSIM_OK;
 }
@@ -157,6 +162,7 @@ extern "C" int smplsim_destroy(SmplsimHandle* h) {
   cudaFree(h->dimg);
   cudaFree(h->gscr);
   cudaFree(h->gsens);
+  cudaFree(h->gpfl);
   delete h;
   return SMPLSIM_OK;
 }
@@ -187,7 +193,7 @@ extern "C" int smplsim_step(SmplsimHandle* h, const SmplsimState* st, const floa
   LStepArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
   a.action = action_dev; a.obs = obs_dev; a.reward = reward_dev; a.terminated = terminated_dev; a.truncated = truncated_dev;
-  a.gscr = h->gscr; a.n = h->num_envs; a.nsub = h->img.hdr()->cfg.nsubsteps; a.mode = 0;
+  a.gscr = h->gscr; a.gpfl = h->gpfl; a.n = h->num_envs; a.nsub = h->img.hdr()->cfg.nsubsteps; a.mode = 0;
   a.gsens = want_sens(h, aux) ? h->gsens : nullptr;
   L_DISPATCH(h, run_step<C_>(h, a, (cudaStream_t)stream));
   CUDA_TRY(cudaGetLastError());
@@ -199,7 +205,7 @@ extern "C" int smplsim_mj_step(SmplsimHandle* h, const SmplsimState* st, const f
   DeviceGuard guard(h->device);
   LStepArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
-  a.action = ctrl_dev; a.gscr = h->gscr; a.n = h->num_envs; a.nsub = nsub; a.mode = 1;
+  a.action = ctrl_dev; a.gscr = h->gscr; a.gpfl = h->gpfl; a.n = h->num_envs; a.nsub = nsub; a.mode = 1;
   a.gsens = want_sens(h, aux) ? h->gsens : nullptr;
   L_DISPATCH(h, run_step<C_>(h, a, (cudaStream_t)stream));
   CUDA_TRY(cudaGetLastError());
@@ -217,7 +223,7 @@ extern "C" int smplsim_reset(SmplsimHandle* h, const SmplsimState* st, const uin
   DeviceGuard guard(h->device);
   LResetArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
-  a.mask = mask_dev; a.qpos0 = qpos0_dev; a.qvel0 = qvel0_dev; a.obs = obs_dev; a.gscr = h->gscr; a.n = h->num_envs; a.init_mode = mode;
+  a.mask = mask_dev; a.qpos0 = qpos0_dev; a.qvel0 = qvel0_dev; a.obs = obs_dev; a.gscr = h->gscr; a.gpfl = h->gpfl; a.n = h->num_envs; a.init_mode = mode;
   a.gsens = want_sens(h, aux) ? h->gsens : nullptr;
   L_DISPATCH(h, run_reset<C_>(h, a, (cudaStream_t)stream));
   CUDA_TRY(cudaGetLastError());
@@ -280,3 +286,16 @@ extern "C" int smplsim_gae(const float* rewards_dev, const float* not_done_dev, 
   CUDA_TRY(cudaGetLastError());
   return SMPLSIM_OK;
 }
+
+#ifdef SMPLSIM_STATS
+extern "C" int smplsim_debug_stats(int* out32, int reset) {
+#ifdef SMPLSIM_EMU
+  for (int i = 0; i < 32; i++) { out32[i] = g_lstats[i]; if (reset) g_lstats[i] = 0; }
+#else
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32, g_lstats, sizeof(int) * 32);
+  if (reset) { int z[32] = {0}; cudaMemcpyToSymbol(g_lstats, z, sizeof z); }
+#endif
+  return 0;
+}
+#endif
