@@ -40,16 +40,33 @@ WORKLOADS = {
                     desc="cfg2 variant: self_obs_v=2 (obs 361), 4096 SMPL envs/GPU"),
     "cfg3": dict(env="reach", robot="smpl_humanoid", overrides={"env.self_obs_v": 2, "robot.create_vel_sensors": True}, envs=16384, balg=2974,
                  desc="cfg3: 16384 SMPL envs/GPU, env=reach, self_obs_v=2 (obs 361), uhc_pd"),
+    "cfg4": dict(env="speed", robot="smpl_humanoid", overrides={"env.self_obs_v": 2, "robot.create_vel_sensors": True}, envs=8192, balg=2958 + 4 * (76 + 75) * 2,
+                 motion=True,
+                 desc="cfg4 shard: 8192 SMPL envs/GPU (65 536 on 8), obs_v2=361, per-step get_motion_state_intervaled gather of the reference pose "
+                      "(synthetic clip tables, SURVEY 8d) + MoCap reset of finished envs from the gathered frame, uhc_pd"),
     "cfg5": dict(env="getup", robot="smplx_humanoid", overrides={}, envs=4096, balg=5698,
                  desc="cfg5 shard: 4096 SMPL-X (52 bodies) envs/GPU, env=getup (Fall init), obs_v1, uhc_pd"),
 }
 _WL = "cfg2"
 
 
-def make_cfg():
+def make_cfg(wl=None):
     from smplsim_b200.cfg import make_cfg as mk
-    w = WORKLOADS[_WL]
+    w = WORKLOADS[wl or _WL]
     return mk(env=w["env"], robot=w["robot"], overrides=w["overrides"])
+
+
+PEAK_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FP32 lanes x 2 (FMA) x clocks.max.sm: 74.5 TFLOP/s nominal
+
+
+def kernel_counters():
+    """ncu counters of the dominant kernel (profiles/k_step5_counters.json, written from the committed ncu capture):
+    issue-slot utilisation, active threads per instruction, resident warps, FP32 operations per env-step."""
+    p = os.path.join(ROOT, "profiles", "k_step5_counters.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -144,16 +161,8 @@ class CpuOracle:
         self.logical = os.cpu_count() or 1
         self.rng = np.random.default_rng(0)
         self.per_step = None
-        if threads is None:          # the stronger of {quota, 2 x quota} threads (measured on the B200 box: 16-CPU quota, 32 threads best)
-            hc = host_cores()
-            best = None
-            for th in sorted({hc, min(2 * hc, self.logical)}):
-                self._setup(th)
-                self.run(2)
-                rate = self.nenv * 6 / self.run(6)
-                if best is None or rate > best[0]:
-                    best = (rate, th)
-            threads = best[1]
+        if threads is None:          # fixed rule, no calibration: one pthread per host core this process may use (affinity / cgroup quota)
+            threads = host_cores()
         self._setup(threads)
 
     def _setup(self, threads):
@@ -177,7 +186,7 @@ class CpuOracle:
         nsteps = int(max(2, min(4000, seconds_target / self.per_step)))
         t = self.run(nsteps)
         self.per_step = t / nsteps
-        return dict(value=self.nenv * nsteps / t, unit="env-steps/s", cores=self.cores, kind="port",
+        return dict(value=self.nenv * nsteps / t, unit="env-steps/s", cores=self.cores, per_core=self.nenv * nsteps / t / self.cores, kind="port",
                     sample=f"{self.nenv} envs x {nsteps} env-steps ({self.nenv * nsteps} env-steps, {t:.1f} s) of the cfg2 workload, "
                            f"fp64 oracle port, {self.cores} pthreads (affinity / cgroup quota; {self.logical} logical CPUs visible)")
 
@@ -215,42 +224,25 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    args = ap.parse_args()
-    global _WL, WORKLOAD, B_ALG_BYTES
-    _WL = args.workload
-    WORKLOAD, B_ALG_BYTES = WORKLOADS[_WL]["desc"], WORKLOADS[_WL]["balg"]
-    if args.envs_per_gpu == ENVS_PER_GPU:
-        args.envs_per_gpu = WORKLOADS[_WL]["envs"]
-    if args.impl == "reference":
-        return run_reference(args)
-
-    import torch
-    import torch.distributed as dist
+def measure(wl, args, torch, dist, world, rank, local, K, W, headline):
+    """One workload on this rank's GPU: device-resident throughput, kernel time, end-to-end with host buffers (headline only)."""
     from smplsim_b200.batched import HumanoidBatchB200
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    N, K, W = args.envs_per_gpu, args.steps, max(3, args.warmup)
-    cfg = make_cfg()
+    spec = WORKLOADS[wl]
+    N = args.envs_per_gpu if headline else spec["envs"]
+    cfg = make_cfg(wl)
     env = HumanoidBatchB200(cfg, num_envs=N, device=str(dev), seed=0, rank=rank, with_aux=False)
     nu = env.num_actions
     gen = torch.Generator(device=dev)
     gen.manual_seed(0 + rank)
+    motion = bool(spec.get("motion"))
+    lib = None
+    if motion:
+        from smplsim_b200.motion_lib import MotionLibB200, synthetic_tables
+        lib = MotionLibB200(env, synthetic_tables(env, num_clips=64, frames=300))
+        ids = (torch.arange(N, device=dev) % 64).to(torch.int32)
+        t_env = torch.rand(N, generator=gen, device=dev) * 8.0
+        dt = float(env.dt)
 
     def draw(k):
         return torch.clamp(torch.randn(k, N, nu, generator=gen, device=dev) * SIGMA, -1, 1)
@@ -262,25 +254,47 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    env.reset()
+    def one_step(a):
+        if motion:   # reference-pose feed of the step (motion_lib_base.py:313-354), then the step, then MoCap reset of finished envs
+            st = lib.get_motion_state_intervaled(ids, t_env)
+            env.step(a)
+            env.reset(env.reset_buf, init_mode=2, qpos0=st["qpos"], qvel0=st["qvel"])
+            t_env.add_(dt)
+            t_env.masked_fill_(t_env > 9.0, 0.0)
+        else:
+            env.step(a); env.reset_done()
+
+    if motion:
+        st0 = lib.get_motion_state_intervaled(ids, t_env)
+        env.reset(None, init_mode=2, qpos0=st0["qpos"], qvel0=st0["qvel"])
+    else:
+        env.reset()
     acts = draw(W)
     for i in range(W):
-        env.step(acts[i]); env.reset_done(); flush.zero_()
+        one_step(acts[i]); flush.zero_()
     # ---------------- timed region 1: device-resident inputs ("value")
     acts = draw(K)
     launches0 = env.gpu_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and headline:
         sampler.start()
     barrier()
     ev0.record()
     for i in range(K):
-        env.step(acts[i]); env.reset_done(); flush.zero_()
+        one_step(acts[i]); flush.zero_()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = env.gpu_launches - launches0
+    # ---------------- the L2 flush alone (it sits inside the timed region above: `value` is conservative by this much)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(10):
+        flush.zero_()
+    f1.record()
+    torch.cuda.synchronize()
+    flush_ms = f0.elapsed_time(f1) / 10
     # ---------------- per-kernel timing of k_step for the roofline (events on the launching stream)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 50))]
     for i, (a, b) in enumerate(kev):
@@ -289,41 +303,91 @@ def main():
         env.reset_done()
     torch.cuda.synchronize()
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    # ---------------- timed region 2: end to end through the public API with HOST buffers ("e2e")
-    h_act = [torch.clamp(torch.randn(N, nu) * SIGMA, -1, 1).pin_memory() for _ in range(4)]
-    h_obs = torch.empty(N, env.num_obs).pin_memory()
-    h_rew = torch.empty(N).pin_memory()
-    h_term = torch.empty(N, dtype=torch.uint8).pin_memory()
-    h_trunc = torch.empty(N, dtype=torch.uint8).pin_memory()
-    Ke = min(K, 100)
+    e2e_ms, Ke = 0.0, 0
+    if headline:
+        # ---------------- timed region 2: end to end through the public API with HOST buffers ("e2e")
+        h_act = [torch.clamp(torch.randn(N, nu) * SIGMA, -1, 1).pin_memory() for _ in range(4)]
+        h_obs = torch.empty(N, env.num_obs).pin_memory()
+        h_rew = torch.empty(N).pin_memory()
+        h_term = torch.empty(N, dtype=torch.uint8).pin_memory()
+        h_trunc = torch.empty(N, dtype=torch.uint8).pin_memory()
+        Ke = min(K, 100)
 
-    def e2e_step(i):
-        a = h_act[i % 4].to(dev, non_blocking=True)
-        obs, rew, term, trunc = env.step(a)
-        h_obs.copy_(obs, non_blocking=True); h_rew.copy_(rew, non_blocking=True)
-        h_term.copy_(term, non_blocking=True); h_trunc.copy_(trunc, non_blocking=True)
-        env.reset_done()
-        flush.zero_()
-        torch.cuda.current_stream().synchronize()       # the caller owns the host results before the next step
+        def e2e_step(i):
+            a = h_act[i % 4].to(dev, non_blocking=True)
+            obs, rew, term, trunc = env.step(a)
+            h_obs.copy_(obs, non_blocking=True); h_rew.copy_(rew, non_blocking=True)
+            h_term.copy_(term, non_blocking=True); h_trunc.copy_(trunc, non_blocking=True)
+            env.reset_done()
+            flush.zero_()
+            torch.cuda.current_stream().synchronize()       # the caller owns the host results before the next step
 
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for i in range(Ke):
-        e2e_step(i)
-    e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    clocks = sampler.stop() if rank == 0 else None
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(Ke):
+            e2e_step(i)
+        e1.record()
+        barrier()
+        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    clocks = sampler.stop() if (rank == 0 and headline) else None
     # ---------------- max over ranks
-    t = torch.tensor([ms, e2e_ms, k_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_ms, k_ms, flush_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, k_ms = [float(x) for x in t.tolist()]
+    ms, e2e_ms, k_ms, flush_ms = [float(x) for x in t.tolist()]
+    out = dict(N=N, K=K, ms=ms, e2e_ms=e2e_ms, Ke=Ke, k_ms=k_ms, flush_ms=flush_ms, launches=launches, clocks=clocks, env=env, cfg=cfg)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extra", action="store_true", help="skip the short cfg4 / cfg5 runs appended to the headline line")
+    args = ap.parse_args()
+    global _WL, WORKLOAD, B_ALG_BYTES
+    _WL = args.workload
+    WORKLOAD, B_ALG_BYTES = WORKLOADS[_WL]["desc"], WORKLOADS[_WL]["balg"]
+    if args.envs_per_gpu == ENVS_PER_GPU:
+        args.envs_per_gpu = WORKLOADS[_WL]["envs"]
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    K, W = args.steps, max(3, args.warmup)
+    r = measure(_WL, args, torch, dist, world, rank, local, K, W, True)
+    env, cfg, N = r["env"], r["cfg"], r["N"]
+    extra = {}
+    if not args.no_extra and _WL == "cfg2":
+        # the configurations north_star states its target on (cfg4: 65 536 envs + motion feed on 8 GPUs; cfg5: SMPL-X), short runs
+        for wl in ("cfg4", "cfg5"):
+            Kx = max(10, K // 8)
+            x = measure(wl, args, torch, dist, world, rank, local, Kx, 3, False)
+            extra[wl] = {"workload": WORKLOADS[wl]["desc"], "envs_per_gpu": x["N"], "global_envs": x["N"] * world, "steps": Kx,
+                         "value": x["N"] * world * Kx / (x["ms"] * 1e-3), "unit": "env-steps/s", "ms_per_step": x["ms"] / Kx,
+                         "kernel_ms": x["k_ms"], "gpu_launches": x["launches"], "smem_bytes_per_env": x["env"].smem_bytes_per_env()}
+            del x
     if rank == 0:
+        ms, e2e_ms, k_ms, Ke = r["ms"], r["e2e_ms"], r["k_ms"], r["Ke"]
+        nu = env.num_actions
         total_envs = N * world
         value = total_envs * K / (ms * 1e-3)
         e2e = total_envs * Ke / (e2e_ms * 1e-3)
@@ -331,12 +395,17 @@ def main():
         balg = B_ALG_BYTES + (B_ALG_STALE_BYTES if env.envcfg.spd_stale and env.envcfg.control_mode == 0 else 0)
         achieved = balg * N / (k_ms * 1e-3) / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "k_step_dram_bytes.json")
-        if os.path.exists(tp) and _WL == "cfg2":
-            try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        kc = kernel_counters() if _WL == "cfg2" else None
+        secondary = None
+        if kc:
+            traffic = kc.get("dram_bytes_per_launch")
+            flops = kc.get("fp32_flops_per_env_step")
+            secondary = {"issue_active_pct": kc.get("issue_active_pct"), "threads_per_inst": kc.get("threads_per_inst"),
+                         "warps_per_sm": kc.get("warps_per_sm"), "warp_inst_per_env_step": kc.get("warp_inst_per_env_step"),
+                         "fp32_flops_per_env_step": flops,
+                         "fp32_tflops": (flops * N / (k_ms * 1e-3) / 1e12) if flops else None,
+                         "fp32_flop_frac": (flops * N / (k_ms * 1e-3) / 1e12 / PEAK_FP32_TFLOPS) if flops else None,
+                         "fp32_peak_tflops": PEAK_FP32_TFLOPS, "source": kc.get("source")}
         line = {
             "metric": "env-steps/sec SMPL humanoid (speed task, 15 substeps/step)", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -344,15 +413,20 @@ def main():
             "config": {"workload": WORKLOAD, "envs_per_gpu": N, "global_envs": total_envs, "substeps_per_step": int(env.envcfg.nsubsteps),
                        "control_mode": str(cfg.env.control_mode), "spd_inertia": "stale" if env.envcfg.spd_stale else "fresh", "parallelism": f"env-shard x{world}",
                        "kernel": f"v{env.kernel_version}", "smem_bytes_per_env": env.smem_bytes_per_env(),
-                       "l2": "256 MiB flush buffer zeroed after every step inside the timed region (state ~11 MB < 126 MB L2)"},
+                       "l2": "256 MiB flush buffer zeroed after every step inside the timed region (state ~11 MB < 126 MB L2)",
+                       "flush_ms_per_step": r["flush_ms"], "value_excluding_flush": total_envs * K / (max(ms - K * r["flush_ms"], 1e-9) * 1e-3)},
             "substeps_per_s": value * int(env.envcfg.nsubsteps),
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": N * nu * 4, "d2h_bytes_per_step": N * (env.num_obs * 4 + 4 + 2),
                     "steps": Ke, "note": "pinned host actions -> device, step, obs/reward/flags -> pinned host, stream sync every step"},
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": r["launches"], "clocks": r["clocks"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": f"k_step{env.kernel_version}" if env.kernel_version > 1 else "k_step", "kernel_ms": k_ms, "alg_bytes_per_env_step": balg,
-                         "note": "15 fused substeps keep state on-chip: the kernel is FP32-issue/latency bound, not HBM bound (SURVEY.md 8d)"},
+                         "peak_source": peak_src, "kernel": f"k_step{env.kernel_version}", "kernel_ms": k_ms, "alg_bytes_per_env_step": balg,
+                         "secondary": secondary,
+                         "note": "15 fused substeps keep state on-chip: the kernel is FP32-issue / latency bound, not HBM bound (SURVEY.md 8d); "
+                                 "`secondary` carries the issue-slot and FP32 fractions"},
         }
+        if extra:
+            line["other_workloads"] = extra
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_oracle_throughput()
         print(json.dumps(line), flush=True)
