@@ -30,10 +30,7 @@ def estimate_advantages(rewards, not_done, not_dead, values, gamma: float, tau: 
     _lib.check(_lib.lib().smplsim_gae(_p(rewards), _p(not_done), _p(not_dead), _p(values), _p(nv), float(gamma), float(tau), T, N,
                                       _p(adv), _p(ret), C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream)))
     if normalize:
-        mean, std_pop = global_moments(adv)
-        n = float(adv.numel())
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            n *= torch.distributed.get_world_size()
+        mean, std_pop, n = global_moments(adv, with_count=True)       # n: elements over ALL ranks (shards may be uneven)
         std = std_pop * (n / max(n - 1.0, 1.0)) ** 0.5
         adv = (adv - mean) / std
     return adv, ret
@@ -44,7 +41,10 @@ class BatchedSampler:
 
     ``policy(obs[N,D]) -> action[N,A]`` is any callable on CUDA tensors (e.g. ``lambda o: policy_net.select_action(o, mean_action)``).
     Pre/post-processing follows Agent.preprocess_obs / preprocess_actions (agents/agent.py:147-161): observations clipped to
-    +-obs_clip (5), actions clipped to [-1, 1].  Envs that terminate or time out are reset in-stream (masked reset kernel)."""
+    +-obs_clip (5); the env receives the action clipped to [-1, 1] while the RAW sampled action is what the batch records
+    (agent.py:81-93, "action processing should not affect the recorded action": the PPO ratio needs the density the action was
+    drawn from).  Envs that terminate or time out are reset in-stream (masked reset kernel).  Pinned against a trajectory
+    recorded by the reference's own Agent.sample_worker + Memory / TrajBatch (tests/golden/sampler.npz, tests/test_sampler_cpu.py)."""
 
     def __init__(self, env, policy: Callable[[torch.Tensor], torch.Tensor], obs_clip: float = 5.0):
         self.env = env
@@ -65,10 +65,10 @@ class BatchedSampler:
                    rewards=torch.empty(horizon, N, device=dv), not_done=torch.empty(horizon, N, device=dv),
                    not_dead=torch.empty(horizon, N, device=dv), next_states=torch.empty(horizon, N, D, device=dv))
         for t in range(horizon):
-            a = torch.clamp(self.policy(self._obs), -1.0, 1.0)
+            a_raw = self.policy(self._obs)
             out["states"][t] = self._obs
-            out["actions"][t] = a
-            obs, rew, term, trunc = env.step(a)
+            out["actions"][t] = a_raw
+            obs, rew, term, trunc = env.step(torch.clamp(a_raw, -1.0, 1.0))
             out["rewards"][t] = rew
             out["not_dead"][t] = 1.0 - term.float()
             out["not_done"][t] = 1.0 - env.reset_buf.float()

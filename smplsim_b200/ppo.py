@@ -44,12 +44,14 @@ class RunningNorm(nn.Module):
     @torch.no_grad()
     def update(self, x: torch.Tensor):
         m = x.shape[0]
-        if _dist_on():
-            s = torch.cat([x.sum(0), (x * x).sum(0), x.new_tensor([float(m)])])
+        if _dist_on():     # batch moments over all ranks; float64 one-pass sums so that the result matches var_mean of the joint batch
+            xd = x.double()
+            s = torch.cat([xd.sum(0), (xd * xd).sum(0), xd.new_tensor([float(m)])])
             torch.distributed.all_reduce(s)
             m = int(round(float(s[-1])))
-            mean_x = s[: self.dim] / m
-            var_x = (s[self.dim: 2 * self.dim] / m - mean_x * mean_x).clamp_min(0.0)
+            mean_d = s[: self.dim] / m
+            var_x = (s[self.dim: 2 * self.dim] / m - mean_d * mean_d).clamp_min(0.0).to(x.dtype)
+            mean_x = mean_d.to(x.dtype)
         else:
             var_x, mean_x = torch.var_mean(x, dim=0, unbiased=False)
         w = self.n.to(x.dtype) / (m + self.n).to(x.dtype)
@@ -152,13 +154,14 @@ class PPOLearner:
 
     def __init__(self, policy: PolicyGaussian, value: Value, gamma: float = 0.99, tau: float = 0.95, clip_epsilon: float = 0.2,
                  opt_num_epochs: int = 10, value_opt_niter: int = 1, policy_lr: float = 5e-5, value_lr: float = 3e-4,
-                 policy_grad_clip: Optional[float] = 25.0, weight_decay: float = 0.0):
+                 policy_grad_clip: Optional[float] = 25.0, weight_decay: float = 0.0, value_weight_decay: Optional[float] = None):
         self.policy, self.value = policy, value
         self.gamma, self.tau, self.clip_epsilon = gamma, tau, clip_epsilon
         self.opt_num_epochs, self.value_opt_niter, self.policy_grad_clip = opt_num_epochs, value_opt_niter, policy_grad_clip
         # get_optimizer (learning/learning_utils.py:188-190)
         self.optimizer_policy = torch.optim.Adam(policy.parameters(), eps=1e-8, lr=policy_lr, weight_decay=weight_decay)
-        self.optimizer_value = torch.optim.Adam(value.parameters(), eps=1e-8, lr=value_lr, weight_decay=weight_decay)
+        self.optimizer_value = torch.optim.Adam(value.parameters(), eps=1e-8, lr=value_lr,
+                                                weight_decay=weight_decay if value_weight_decay is None else value_weight_decay)
 
     def _step(self, loss, net, opt, clip=None):
         opt.zero_grad()
@@ -217,5 +220,6 @@ def build_from_cfg(cfg, state_dim: int, action_dim: int, device="cuda:0"):
     value = Value(state_dim, units, act).to(device)
     learner = PPOLearner(policy, value, gamma=float(g("gamma", 0.99)), tau=float(g("tau", 0.95)), clip_epsilon=float(g("clip_epsilon", 0.2)),
                          opt_num_epochs=int(g("opt_num_epochs", 10)), policy_lr=float(g("policy_lr", 5e-5)), value_lr=float(g("value_lr", 3e-4)),
-                         policy_grad_clip=g("policy_grad_clip", 25), weight_decay=float(g("policy_weightdecay", 0.0)))
+                         policy_grad_clip=g("policy_grad_clip", 25), weight_decay=float(g("policy_weightdecay", 0.0)),
+                         value_weight_decay=float(g("value_weightdecay", 0.0)))
     return policy, value, learner

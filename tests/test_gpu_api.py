@@ -112,7 +112,7 @@ def test_smplx_env_step_matches_oracle():
     """BASELINE config 5 model (52 bodies, 159 dofs): getup env step vs the oracle."""
     from smplsim_b200.batched import HumanoidBatchB200
     cfg = make_cfg(env="getup", robot="smplx_humanoid", seed=5)
-    n = 4
+    n = 8
     env = HumanoidBatchB200(cfg, num_envs=n, seed=5)
     assert env.num_obs == 626 and env.num_actions == 153
     obs0 = env.reset().cpu().numpy().copy()
@@ -125,7 +125,7 @@ def test_smplx_env_step_matches_oracle():
         o0 = e.reset()
         assert np.abs(o0 - obs0[i]).max() < 5e-3
         o, r, te, tr = e.step(act[i])
-        assert np.abs(o - obs[i]).max() < 1e-2 and abs(r - rew[i]) < 1e-3
+        assert np.abs(o - obs[i]).max() < 1e-3 and abs(r - rew[i]) < 1e-3      # one env step = 15 substeps from the Fall-init pose
 
 
 def test_gae_matches_reference_golden():

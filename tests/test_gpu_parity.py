@@ -13,7 +13,7 @@ import pytest
 torch = pytest.importorskip("torch")
 from conftest import GOLDEN  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
-from util_states import airborne_states, make_models, relerr, rollout_states  # noqa: E402
+from util_states import airborne_states, elem_relerr, make_models, relerr, rollout_states  # noqa: E402
 
 TOL = 1e-4
 
@@ -99,14 +99,21 @@ def test_free_fall_closed_form(backend):
     assert np.abs(gv[:, 6:]).max() < 1e-4 and np.abs(gv[:, [0, 1, 3, 4, 5]]).max() < 1e-4
 
 
-@pytest.mark.parametrize("mode", ["torque", "uhc_pd"])
-def test_mj_step_contact_states(backend, mode):
-    """One substep from standing / stumbling / fallen states: qpos, qvel to 1e-4, contact geom flags bit-exact
-    (outside a |dist - margin| < 1e-5 guard band), through mj_step with the oracle's own torque."""
-    cfg, om = make_models(control_mode=mode)
+@pytest.mark.parametrize("robot,mode", [("smpl_humanoid", "torque"), ("smpl_humanoid", "uhc_pd"), ("smplx_humanoid", "torque")])
+def test_mj_step_contact_states(backend, robot, mode):
+    """One substep from standing / stumbling / fallen states, through mj_step with the oracle's own torque.
+    qpos, qvel: norm-relative 1e-4 (max|d| / max(1, max|x|)) AND per-element relative error with a stated floor
+    (|d_i| / max(|x_i|, floor); floors: qvel 1 rad/s, qpos 1 -- one fp32 ABA solve through contact rows of stiffness ~1e4 loses
+    ~3 digits, so velocity components far below the step's own velocity change h max|qacc| ~ 15 rad/s cannot be resolved
+    better than 2e-3 of the floor); qacc norm-relative 5e-4.  Contact geom flags bit-exact outside a |dist - margin| < 1e-5
+    guard band; at most 10 % of the states may fall into the band.  The solver may neither drop rows nor hit its iteration cap.
+    SMPL-X (52 bodies, 1 g finger links behind a 1e4 N/m contact) is held to 2e-4: the fp32 articulated-inertia recursion loses
+    one more bit there (the SMPL model named by north_star stays at 1e-4)."""
+    tol = TOL if robot == "smpl_humanoid" else 2e-4
+    cfg, om = make_models(robot=robot, control_mode=mode)
     m = om.model
-    n = 96
-    q, v, w = rollout_states(make_models(control_mode="uhc_pd")[1], n, seed=11)   # states from stable-PD rollouts
+    n = 96 if robot == "smpl_humanoid" else 48
+    q, v, w = rollout_states(make_models(robot=robot, control_mode="uhc_pd")[1], n, seed=11)   # states from stable-PD rollouts
     rng = np.random.default_rng(2)
     ctrl = rng.uniform(-80, 80, (n, m.nu))
     env = backend.batch(cfg, n)
@@ -116,28 +123,37 @@ def test_mj_step_contact_states(backend, mode):
     gq, gv, ga = env.qpos.cpu().numpy(), env.qvel.cpu().numpy(), env.qacc.cpu().numpy()
     gmask = env.contact_mask.cpu().numpy().astype(np.uint64)
     it = env.solver_iter.cpu().numpy()
-    ncontact_states = 0
-    worst = 0.0
+    st = env.status.cpu().numpy()
+    assert not (st & (8 | 16)).any(), ("rows dropped / iteration cap", st)
+    ncontact_states = nguard = nexact = 0
+    worst = worst_el = 0.0
     for i in range(n):
         e = _oracle_one_step(om, q[i], v[i], w[i], ctrl[i])
         con = e.contacts()
         guard = (np.abs(con["dist"] - m.margin) < 1e-5).any() if e.ncon else False
-        # near-margin geoms that the oracle rejected are also guard cases: recheck with a tiny margin change is overkill;
         # flags must match whenever no contact sits inside the band
         if not guard and int(gmask[i]) != e.contact_mask:
             # tolerate a geom whose nearest feature is within the band on the rejecting side
             diff = int(gmask[i]) ^ e.contact_mask
             assert _near_margin(om, q[i], diff), ("contact flags", i, bin(int(gmask[i])), bin(e.contact_mask))
+            nguard += 1
             continue
         if guard:
+            nguard += 1
             continue
+        nexact += 1
         ncontact_states += e.ncon > 0
         worst = max(worst, relerr(gv[i], e.qvel), relerr(gq[i], e.qpos))
-        assert relerr(gv[i], e.qvel) < TOL, ("qvel", i, relerr(gv[i], e.qvel), e.ncon, int(it[i]), e.solver_iter)
-        assert relerr(gq[i], e.qpos) < TOL, ("qpos", i, relerr(gq[i], e.qpos))
-        assert relerr(ga[i], e.qacc) < 2e-2, ("qacc", i, relerr(ga[i], e.qacc), e.ncon)
-    assert ncontact_states > n // 2
-    print(f"worst relerr {worst:.2e} over {ncontact_states} contact states; max solver iters {it.max()}")
+        worst_el = max(worst_el, elem_relerr(gv[i], e.qvel, 1.0), elem_relerr(gq[i], e.qpos, 1.0))
+        assert relerr(gv[i], e.qvel) < tol, ("qvel", i, relerr(gv[i], e.qvel), e.ncon, int(it[i]), e.solver_iter)
+        assert relerr(gq[i], e.qpos) < tol, ("qpos", i, relerr(gq[i], e.qpos))
+        assert elem_relerr(gv[i], e.qvel, 1.0) < 20 * tol, ("qvel per element", i, elem_relerr(gv[i], e.qvel, 1.0))
+        assert elem_relerr(gq[i], e.qpos, 1.0) < 1e-5, ("qpos per element", i, elem_relerr(gq[i], e.qpos, 1.0))
+        assert relerr(ga[i], e.qacc) < 5e-4, ("qacc", i, relerr(ga[i], e.qacc), e.ncon)
+    assert nguard <= n // 10, f"{nguard} of {n} states skipped for a contact inside the guard band"
+    assert nexact >= n - n // 10 and ncontact_states > n // 3
+    print(f"{robot}/{mode}: {nexact} states compared with bit-exact flags ({nguard} in the guard band), {ncontact_states} with contacts; "
+          f"worst norm-relative {worst:.2e}, worst per-element (floor 1) {worst_el:.2e}; max solver iters {it.max()}")
 
 
 def _near_margin(om, q, diffmask):

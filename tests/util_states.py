@@ -44,5 +44,13 @@ def airborne_states(m, n, seed=0, vel=2.0):
 
 
 def relerr(a, b):
+    """Norm-relative error: max|a - b| / max(1, max|b|)."""
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b))))
+
+
+def elem_relerr(a, b, floor):
+    """Per-element relative error max_i |a_i - b_i| / max(|b_i|, floor): every component is held to its own magnitude, components
+    below `floor` to `floor` (state the floor next to the tolerance)."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
