@@ -152,7 +152,7 @@ def test_batched_sampler_shapes_and_masks():
     sampler = BatchedSampler(env, lambda o: o @ W)
     b = sampler.sample(T)
     assert b["states"].shape == (T, n, 292) and b["actions"].shape == (T, n, 69) and b["rewards"].shape == (T, n)
-    assert b["states"].abs().max() <= 5.0 and b["actions"].abs().max() <= 1.0
+    assert b["states"].abs().max() <= 5.0            # observations clipped; the RAW action is recorded (agent.py:81-93), see test_sampler_cpu.py
     nd = b["not_done"].cpu().numpy()
     assert (nd[5] == 0).all() and (nd[:5] == 1).all()            # cur_t = 6 > 5 at the 6th step: every env truncates together
     assert torch.equal(b["states"][6, :, 0], torch.full((n,), 0.94, device="cuda:0"))   # next state after the in-stream reset
