@@ -343,6 +343,52 @@ def measure(wl, args, torch, dist, world, rank, local, K, W, headline):
     return out
 
 
+def measure_ppo(torch, dist, world, rank, local, horizon=12, iters=2):
+    """The one collective of the project: a PPO iteration = device-resident rollout of `horizon` steps over this
+    rank's 4 096 envs (policy forward included) -> GAE -> AgentPPO.update_params (10 full-batch epochs, the reference's 6-layer
+    2048...512 MLP) with the gradients averaged over ranks by bucketed asynchronous NCCL all-reduces.  Max over ranks."""
+    from smplsim_b200.batched import HumanoidBatchB200
+    from smplsim_b200.cfg import make_cfg as mk
+    from smplsim_b200.dist import rank_seed
+    from smplsim_b200.learning import BatchedSampler
+    from smplsim_b200.ppo import PolicyGaussian, PPOLearner, Value
+    dev = torch.device(f"cuda:{local}")
+    N = 4096
+    units = [2048, 1536, 1024, 1024, 512, 512]           # data/cfg/learning/simple_mlp.yaml
+    torch.manual_seed(0)
+    env = HumanoidBatchB200(mk(env="speed"), num_envs=N, device=str(dev), seed=0, rank=rank, with_aux=False)
+    policy = PolicyGaussian(env.num_obs, env.num_actions, units, "silu", -2.5, True).to(dev)
+    value = Value(env.num_obs, units, "silu").to(dev)
+    learner = PPOLearner(policy, value)
+    gen = torch.Generator(device=dev); gen.manual_seed(rank_seed(0, rank))
+
+    def act(obs):
+        policy.eval()
+        return policy.select_action(obs, generator=gen)
+
+    sampler = BatchedSampler(env, act)
+    ts, tu = [], []
+    for it in range(iters + 1):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        batch = sampler.sample(horizon)
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        learner.update(batch)
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+        if it > 0:
+            ts.append(t1 - t0); tu.append(t2 - t1)
+    t = torch.tensor([float(np.mean(ts)), float(np.mean(tu))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s_s, u_s = [float(x) for x in t.tolist()]
+    nparam = sum(p.numel() for p in policy.parameters()) + sum(p.numel() for p in value.parameters())
+    return {"workload": f"PPO iteration: {horizon}-step rollout x {N} envs/GPU (policy forward on device) + GAE + 10 full-batch epochs, MLP {units}",
+            "samples_per_iter": horizon * N * world, "sample_s": s_s, "update_s": u_s, "sample_env_steps_per_s": horizon * N * world / s_s,
+            "iter_samples_per_s": horizon * N * world / (s_s + u_s), "grad_bytes_allreduced_per_epoch": 4 * nparam if world > 1 else 0,
+            "collective": "NCCL all-reduce of policy+value gradients (per-layer buckets, async) and of the advantage / RunningNorm moments"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -385,6 +431,7 @@ def main():
                          "value": x["N"] * world * Kx / (x["ms"] * 1e-3), "unit": "env-steps/s", "ms_per_step": x["ms"] / Kx,
                          "kernel_ms": x["k_ms"], "gpu_launches": x["launches"], "smem_bytes_per_env": x["env"].smem_bytes_per_env()}
             del x
+        extra["ppo"] = measure_ppo(torch, dist, world, rank, local)
     if rank == 0:
         ms, e2e_ms, k_ms, Ke = r["ms"], r["e2e_ms"], r["k_ms"], r["Ke"]
         nu = env.num_actions

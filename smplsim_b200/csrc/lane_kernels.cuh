@@ -1594,13 +1594,28 @@ extern __shared__ float4 l_smem4[];
 template <class C>
 __device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int img_bytes, LLane& w, const float*& ms, int n, float* gscr, float* gsens, int* gpfl) {
   float* smem = L_SMEM;
+  unsigned* slot = (unsigned*)(smem + img_bytes / 4);   // [0] tensor-memory base, [2..3] mbarrier of the table copy
+#ifndef SMPLSIM_EMU
+  {
+    // the constant table arrives as ONE bulk asynchronous copy (TMA engine, cp.async.bulk -> UBLKCP) signalled on an mbarrier,
+    // issued by one thread; it lands while the warps carve their env rows and claim tensor memory
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(slot + 2), dst = (unsigned)__cvta_generic_to_shared(smem);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((unsigned)img_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(gimg), "r"((unsigned)img_bytes), "r"(mb) : "memory");
+    }
+  }
+#else
   {
     const uint4* src = (const uint4*)gimg;
     uint4* dst = (uint4*)smem;
     for (int i = threadIdx.x; i < img_bytes / 16; i += blockDim.x) dst[i] = src[i];
   }
+#endif
   ms = smem;
-  unsigned* slot = (unsigned*)(smem + img_bytes / 4);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   unsigned tbase = 0u;
 #ifndef SMPLSIM_EMU
@@ -1618,6 +1633,13 @@ __device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int im
   __syncthreads();
 #ifndef SMPLSIM_EMU
   if (C::RECT) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {   // every thread waits for the table (phase 0 of the mbarrier)
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(slot + 2);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
+    }
+  }
 #endif
   if (C::RECT) tbase = *slot;
   const int sub = lane / LM_LPE;
