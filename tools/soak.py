@@ -13,7 +13,7 @@ for task, robot, sigma in [("speed", "smpl_humanoid", 0.0821), ("speed", "smpl_h
     ne = n if robot == "smpl_humanoid" else max(n // 4, 64)
     env = HumanoidBatchB200(make_cfg(env=task, robot=robot), num_envs=ne, seed=3)
     env.reset()
-    worst, bad, nres, itmax = 0.0, 0, 0, 0
+    worst, bad, nres, itmax, st8, st16, stbad = 0.0, 0, 0, 0, 0, 0, 0
     for t in range(steps):
         a = torch.clamp(torch.randn(ne, env.num_actions, generator=g, device="cuda:0") * sigma, -1, 1)
         env.step(a)
@@ -22,6 +22,8 @@ for task, robot, sigma in [("speed", "smpl_humanoid", 0.0821), ("speed", "smpl_h
         bad += int((~fin).sum())
         worst = max(worst, float(torch.nan_to_num(qv.abs(), nan=0.0, posinf=0.0).max()))
         itmax = max(itmax, int(env.solver_iter.max()))
+        sb = env.status
+        st8 += int(((sb & 8) != 0).sum()); st16 += int(((sb & 16) != 0).sum()); stbad += int(((sb & 7) != 0).sum())
         nres += int(env.reset_buf.sum())
         env.reset_done()
-    print(f"{task:6s} {robot:15s} sigma {sigma:.3f} envs {ne} steps {steps}: non-finite env-steps {bad}, max|qvel| {worst:.1f}, resets {nres}, max solver iters {itmax}", flush=True)
+    print(f"{task:6s} {robot:15s} sigma {sigma:.3f} envs {ne} steps {steps}: non-finite env-steps {bad}, max|qvel| {worst:.1f}, resets {nres}, max solver iters (last substep) {itmax}, env-steps with rows dropped {st8}, at the iteration cap {st16}, mj_check resets {stbad}", flush=True)
