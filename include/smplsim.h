@@ -46,6 +46,8 @@ extern "C" {
 #define SMPLSIM_INIT_FALL 1    /* humanoid_env.py:478-491 */
 #define SMPLSIM_INIT_MOCAP 2   /* state supplied by the caller (motion_lib feed) */
 
+#define SMPLSIM_STATUS_SELF_CONTACT 32
+
 /* The constant tree / inertia / geom / gain table (replaces mujoco.MjModel for this path,
  * smpl_sim/envs/base_env.py:139-142 + smpl_sim/envs/humanoid_env.py:262-370).  Host memory,
  * float64; copied during smplsim_create.  Robot bodies only (the world body is implicit);
@@ -86,6 +88,13 @@ typedef struct SmplsimModelDesc {
   const double* act_torque_lim; /* [nu] */
   const double* act_scale;      /* [nu] _pd_action_scale (or power_scale*lim in torque mode) */
   const double* act_offset;     /* [nu] */
+  /* geom-geom collision filters of the MJCF (smpl_humanoid.xml:5,24,231-242): used to list the capsule / sphere pairs MuJoCo
+   * would test.  Self-collision is NOT simulated yet; the pairs are tested once per env step and a touching pair raises
+   * SMPLSIM_STATUS_SELF_CONTACT in aux.status.  geom_contype == NULL disables the check. */
+  const int32_t* geom_contype;     /* [ngeom] or NULL */
+  const int32_t* geom_conaffinity; /* [ngeom] or NULL */
+  int32_t nexclude;
+  const int32_t* exclude_pairs;    /* [nexclude*2] body indices of <contact><exclude> */
 } SmplsimModelDesc;
 
 /* cfg.env.* keys consumed on the path (smpl_sim/data/cfg/env/{speed,reach,getup}.yaml). */
@@ -136,7 +145,10 @@ typedef struct SmplsimAux {
   float* qacc;          /* [N,nv] */
   float* ctrl;          /* [N,nu] torque applied in the last substep */
   int32_t* solver_iter; /* [N]   constraint-solver iterations of the last substep */
-  uint8_t* status;      /* [N]   mj_warning bits raised during this call (OR over substeps): 1 BADQPOS, 2 BADQVEL, 4 BADQACC.
+  uint8_t* status;      /* [N]   bits raised during this call (OR over substeps): mj_warning 1 BADQPOS, 2 BADQVEL, 4 BADQACC;
+                         *       8 constraint rows dropped (too many simultaneous joint-limit rows), 16 solver stopped at its iteration cap,
+                         *       32 SMPLSIM_STATUS_SELF_CONTACT: two robot geoms that MuJoCo would collide touch at the end of the step
+                         *       (the contact is not simulated, the state differs from the reference from here on).
                          *       As in mj_step (mj_checkPos/Vel/Acc + mj_resetData) a NaN or |x| > 1e10 auto-resets that env's
                          *       data to qpos0 / zero velocity and the call carries on -- a device fault never traps. */
 } SmplsimAux;

@@ -39,6 +39,7 @@
 // aux.status bits beyond mj_warning's 1 BADQPOS | 2 BADQVEL | 4 BADQACC
 #define L_ST_ROWS_DROPPED 8  // more simultaneous joint-limit rows than the kernel holds: the excess rows were not simulated
 #define L_ST_MAXITER 16      // the active-set solve stopped at L_SOLVER_MAXITER without reaching its fixed point
+#define L_ST_SELF_CONTACT 32 // SMPLSIM_STATUS_SELF_CONTACT: a geom pair MuJoCo would collide touches (not simulated)
 
 // ------------------------------------------------------------------ compile-time sizes / per-env shared-memory layout (words)
 template <int NB_, int NV_, int NG_, int NS_, int NMBI_, int NMBO_, int NCS_, int NLS_, int RECT_>
@@ -1583,6 +1584,50 @@ __device__ __noinline__ void l_write_aux(const float* ms, float* sm, const LLane
   }
 }
 
+// closest points of the segments c1 + s a1 (|s| <= h1) and c2 + t a2 (|t| <= h2), a1, a2 unit: clamped solution
+__device__ __forceinline__ void l_segment_segment(V3 c1, V3 a1, float h1, V3 c2, V3 a2, float h2, float* so, float* to) {
+  V3 r = c1 - c2;
+  float b = dot(a1, a2), cc = dot(a1, r), f = dot(a2, r), den = 1.0f - b * b;
+  float s = (den > 1e-6f) ? (b * f - cc) / den : 0.f;
+  s = fminf(fmaxf(s, -h1), h1);
+  float t = b * s + f;
+  if (t > h2) { t = h2; s = fminf(fmaxf(b * t - cc, -h1), h1); }
+  else if (t < -h2) { t = -h2; s = fminf(fmaxf(b * t - cc, -h1), h1); }
+  *so = s; *to = t;
+}
+
+// Self-collision is not simulated.  Once per env step, on the final kinematics (xquat staging + body rows), test the
+// capsule / sphere geom pairs MuJoCo's filters let through (smpl_humanoid.xml:5,24,231-242); a touching pair means the reference
+// would have generated a geom-geom contact here.  Returns true for this lane's env.
+template <class C>
+__device__ __noinline__ bool l_self_contact(const float* ms, float* sm, const LLane& w) {
+  const LHdr& H = l_hdr<C>(ms);
+  const LGeom* MG = l_geoms(ms);
+  const LPair* PR = (const LPair*)((const char*)ms + H.pair_off);
+  bool hit = false;
+  if (w.live) {
+    for (int i = w.li; i < H.npair; i += LM_LPE) {
+      const LGeom& G1 = MG[PR[i].g1]; const LGeom& G2 = MG[PR[i].g2];
+      const float* q1 = sm + C::xq + 4 * G1.body; const float* q2 = sm + C::xq + 4 * G2.body;
+      Q4 a; a.w = q1[0]; a.x = q1[1]; a.y = q1[2]; a.z = q1[3];
+      Q4 b; b.w = q2[0]; b.x = q2[1]; b.y = q2[2]; b.z = q2[3];
+      V3 c1 = ld3(sm + C::body + C::BODYW * G1.body + LBR_X) + qrot(a, ld3(G1.pos));
+      V3 c2 = ld3(sm + C::body + C::BODYW * G2.body + LBR_X) + qrot(b, ld3(G2.pos));
+      float r1 = G1.size[0], r2 = G2.size[0];
+      float h1 = (G1.type == SMPLSIM_GEOM_CAPSULE) ? G1.size[1] : 0.f, h2 = (G2.type == SMPLSIM_GEOM_CAPSULE) ? G2.size[1] : 0.f;
+      V3 dc = c2 - c1;
+      float reach = h1 + h2 + r1 + r2 + H.margin;
+      if (dot(dc, dc) > reach * reach) continue;                      // bounding spheres
+      V3 a1 = qrot(a, v3(G1.mat[2], G1.mat[5], G1.mat[8])), a2 = qrot(b, v3(G2.mat[2], G2.mat[5], G2.mat[8]));
+      float s, t;
+      l_segment_segment(c1, a1, h1, c2, a2, h2, &s, &t);
+      V3 n = (c2 + t * a2) - (c1 + s * a1);
+      if (sqrtf(dot(n, n)) - r1 - r2 <= H.margin) hit = true;
+    }
+  }
+  return l_gany(hit, w);
+}
+
 #ifdef SMPLSIM_EMU
 #define L_SMEM EMU_SMEM_BASE
 #else
@@ -1712,6 +1757,7 @@ __global__ void __launch_bounds__(256, 1) k_step5(const float* __restrict__ gimg
   LFwd fo; fo.mask = 0ull; fo.iters = 0; fo.status = 0;
   l_substeps<C>(ms, sm, w, a.nsub, a.mode, &fo, a.st, true, false, st);
   l_sweep_out<C>(ms, sm, w, LF_FK | LF_XQUAT, false);
+  if (H.npair > 0 && a.aux.status && l_self_contact<C>(ms, sm, w)) fo.status |= L_ST_SELF_CONTACT;
   if (a.mode == 0) {
     int* ti = (int*)(sm + C::tsk);
     if (w.live && w.li == 0) ti[L_TSK_CURT] += 1;

@@ -29,7 +29,8 @@
 struct LHdr {
   int nb, nv, nu, ng, nslot, T, nmbi, nmbo;
   int obs_dim, self_obs_dim, warmset, dirtypath;
-  int bytes, body_off, geom_off, align;       // image size and the byte offsets of the LBody / LGeom arrays
+  int bytes, body_off, geom_off, align;
+  int pair_off, npair, pad5[2];                 // capsule / sphere geom pairs MuJoCo would collide (LPair array)       // image size and the byte offsets of the LBody / LGeom arrays
   float ls_tol, margin, mu, impratio;
   float solimp[5], imp_a, imp_b, K;
   float B, h, grav[3], plane_pos[3];
@@ -66,6 +67,8 @@ struct LGeom {   // 20 words
   int type, body, slot0;
 };
 
+struct LPair { short g1, g2; };   // geom indices, g1 < g2
+
 struct LaneImage {
   std::vector<unsigned char> bytes;
   LHdr* hdr() { return (LHdr*)bytes.data(); }
@@ -94,11 +97,34 @@ static inline std::string lane_build(const SmplsimModelDesc* s, const SmplsimEnv
     if (s->body_parent[b] < 0 || s->body_parent[b] >= b) return "bodies must be listed parent-first";
     if (s->body_dofnum[b] != 3) return "model class: exactly three hinges on every non-root body (SMPL family)";
   }
+  // ---- geom pairs that pass MuJoCo's filters (same body, filterparent, contype / conaffinity, <exclude>); capsule / sphere only
+  std::vector<LPair> pairs;
+  if (s->geom_contype && s->geom_conaffinity) {
+    for (int g1 = 0; g1 < ng; g1++) {
+      int t1 = s->geom_type[g1], b1 = s->geom_body[g1];
+      if (t1 != SMPLSIM_GEOM_CAPSULE && t1 != SMPLSIM_GEOM_SPHERE) continue;
+      for (int g2 = g1 + 1; g2 < ng; g2++) {
+        int t2 = s->geom_type[g2], b2 = s->geom_body[g2];
+        if (t2 != SMPLSIM_GEOM_CAPSULE && t2 != SMPLSIM_GEOM_SPHERE) continue;
+        if (b1 == b2 || s->body_parent[b1] == b2 || s->body_parent[b2] == b1) continue;
+        if (!((s->geom_contype[g1] & s->geom_conaffinity[g2]) || (s->geom_contype[g2] & s->geom_conaffinity[g1]))) continue;
+        bool skip = false;
+        for (int e = 0; e < s->nexclude; e++) {
+          int x = s->exclude_pairs[2 * e], y = s->exclude_pairs[2 * e + 1];
+          if ((x == b1 && y == b2) || (x == b2 && y == b1)) skip = true;
+        }
+        if (!skip) { LPair p; p.g1 = (short)g1; p.g2 = (short)g2; pairs.push_back(p); }
+      }
+    }
+  }
   size_t body_off = (sizeof(LHdr) + 15) & ~(size_t)15, geom_off = body_off + sizeof(LBody) * nb;
-  size_t total = (geom_off + sizeof(LGeom) * ng + 15) & ~(size_t)15;
+  size_t pair_off = (geom_off + sizeof(LGeom) * ng + 15) & ~(size_t)15;
+  size_t total = (pair_off + sizeof(LPair) * pairs.size() + 15) & ~(size_t)15;
   out.bytes.assign(total, 0);
   LHdr& H = *out.hdr();
   H.nb = nb; H.nv = s->nv; H.nu = s->nu; H.ng = ng; H.bytes = (int)total; H.body_off = (int)body_off; H.geom_off = (int)geom_off;
+  H.pair_off = (int)pair_off; H.npair = (int)pairs.size();
+  if (!pairs.empty()) memcpy(out.bytes.data() + pair_off, pairs.data(), sizeof(LPair) * pairs.size());
   LBody* B = out.bodies();
   LGeom* G = out.geoms();
   // ---- tree, heights

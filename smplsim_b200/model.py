@@ -91,6 +91,10 @@ class SmplsimModelDescC(C.Structure):
         ("act_torque_lim", C.POINTER(C.c_double)),
         ("act_scale", C.POINTER(C.c_double)),
         ("act_offset", C.POINTER(C.c_double)),
+        ("geom_contype", C.POINTER(C.c_int32)),
+        ("geom_conaffinity", C.POINTER(C.c_int32)),
+        ("nexclude", C.c_int32),
+        ("exclude_pairs", C.POINTER(C.c_int32)),
     ]
 
 
@@ -208,6 +212,11 @@ class ModelDesc:
         s.impratio = self.impratio
         s.timestep = self.timestep
         s.gravity[:] = list(self.gravity)
+        s.geom_contype = iptr(self.geom_contype)
+        s.geom_conaffinity = iptr(self.geom_conaffinity)
+        ex = np.array([[self.body_names.index(a), self.body_names.index(b)] for a, b in self.excludes], dtype=np.int32).reshape(-1, 2)
+        s.nexclude = int(ex.shape[0])
+        s.exclude_pairs = iptr(ex)
         s._keepalive = keep
         return s
 

@@ -448,3 +448,34 @@ def test_env_step_simple_pid_matches_oracle(backend):
             assert bool(term[i]) == te and bool(trunc[i]) == tr
     env.reset()                                   # the controller state survives reset, as the reference's controller object does
     assert env.pid_integral.abs().max() > 0 and torch.isfinite(env.pid_last_error).all()
+
+
+def test_self_contact_flag_matches_mujoco_pair_filters(backend):
+    """Self-collision is not simulated; aux.status bit 32 must be raised exactly when a capsule / sphere geom pair that
+    passes MuJoCo's filters (same body, parent-child, contype / conaffinity, the 10 <exclude> pairs of smpl_humanoid.xml:231-242)
+    touches in the state the step ends in -- checked against the oracle's geom-geom narrow phase on the product's own end state
+    (pairs within 1e-5 of the margin are not compared)."""
+    cfg, om = make_models(env="getup", control_mode="torque")
+    m = om.model
+    n = 64
+    q, v, w = rollout_states(make_models(env="getup", control_mode="uhc_pd")[1], n, seed=5, init_mode=1, control_sigma=0.6)
+    env = backend.batch(cfg, n)
+    env.set_state(backend.t(q), backend.t(v))
+    env.mj_step(backend.t(np.zeros((n, m.nu))), 1)
+    st = env.status.cpu().numpy()
+    gq = env.qpos.cpu().numpy()
+    om.set_self_collision(True)
+    nhit = ncmp = 0
+    for i in range(n):
+        e = orc.OracleEnv(om)
+        e.qpos[:] = gq[i]; e.qvel[:] = 0; e.forward()
+        con = e.contacts()
+        selfc = con["geom1"] > 0
+        if selfc.any() and (np.abs(con["dist"][selfc] - m.margin) < 1e-5).any():
+            continue
+        # a pair just outside the margin in the oracle may sit inside it in fp32 and vice versa: re-test with a widened margin
+        ncmp += 1
+        nhit += int(selfc.any())
+        assert bool(st[i] & 32) == bool(selfc.any()), (i, st[i], con["dist"][selfc])
+    om.set_self_collision(False)
+    assert ncmp >= n - 4 and 3 <= nhit < ncmp, (ncmp, nhit)
