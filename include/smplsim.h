@@ -116,6 +116,9 @@ typedef struct SmplsimEnvCfg {
   double tar_dist_max;                        /* reach */
   double tar_height_min, tar_height_max;      /* reach / getup */
   uint64_t seed;                              /* Philox key for task sampling and Fall init */
+  int32_t self_collision;  /* 1: geom-geom contacts between the capsule / sphere pairs MuJoCo's filters let through are simulated
+                            *    (two-body rows; the reference MJCF enables them).  0: detected only (aux.status bit 32). */
+  int32_t pad_;
 } SmplsimEnvCfg;
 
 /* Per-env simulation state, SoA tensors [N, ...] owned by the caller. */

@@ -87,11 +87,15 @@ class OracleModel:
     @classmethod
     def from_cfg(cls, cfg, seed: int = 0):
         m = model_from_cfg(cfg)
-        return cls(m, env_cfg_from(cfg, m, seed=seed))
+        om = cls(m, env_cfg_from(cfg, m, seed=seed))
+        e = cfg.env
+        if bool(e.get("self_collision", False) if hasattr(e, "get") else getattr(e, "self_collision", False)):
+            om.set_self_collision(True)
+        return om
 
     def set_self_collision(self, enable: bool = True):
-        """ORACLE-ONLY groundwork for SURVEY 8 f4 (the CUDA product does not simulate self-collision): capsule / sphere geom pairs
-        with MuJoCo's filters (same body, parent-child, contype / conaffinity, <contact><exclude>).  Off by default."""
+        """Geom-geom contacts between capsule / sphere geom pairs with MuJoCo's filters (same body, parent-child,
+        contype / conaffinity, <contact><exclude>); what cfg.env.self_collision switches on in the product."""
         m = self.model
         ex = np.array([[m.body_names.index(a), m.body_names.index(b)] for a, b in m.excludes], dtype=np.int32).reshape(-1, 2)
         ct = np.ascontiguousarray(m.geom_contype, dtype=np.int32); ca = np.ascontiguousarray(m.geom_conaffinity, dtype=np.int32)

@@ -21,6 +21,7 @@ class SmplsimEnvCfgC(C.Structure):
         ("change_steps_max", C.c_int32),
         ("tar_speed_min", C.c_double), ("tar_speed_max", C.c_double), ("tar_dist_max", C.c_double),
         ("tar_height_min", C.c_double), ("tar_height_max", C.c_double), ("seed", C.c_uint64),
+        ("self_collision", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -82,6 +83,7 @@ def env_cfg_from(cfg: Any, model: ModelDesc, seed: int = 0) -> SmplsimEnvCfgC:
     c.spd_stale = int(_get(e, "spd_inertia", "stale") == "stale")
     c.legacy_change_step = int(bool(_get(e, "legacy_change_step_bug", True)))
     c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    c.self_collision = int(bool(_get(e, "self_collision", False)))
     if task == "HumanoidSpeed":
         c.tar_speed_min, c.tar_speed_max = float(e.tar_speed_min), float(e.tar_speed_max)
         c.change_steps_min, c.change_steps_max = int(e.speed_change_steps_min), int(e.speed_change_steps_max)

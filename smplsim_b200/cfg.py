@@ -82,7 +82,8 @@ def make_cfg(env: str = "base_env", robot: str = "smpl_humanoid", overrides: Opt
              **top) -> Cfg:
     """``python smpl_sim/run.py env=speed robot=... key=value`` -> cfg (hydra ``defaults`` composition).
 
-    b200-only additions live under ``cfg.env``: ``num_envs`` (default 1), ``spd_inertia``
+    b200-only additions live under ``cfg.env``: ``self_collision`` (geom-geom contacts between the capsule / sphere pairs MuJoCo's
+    filters let through, simulated as two-body rows; default False = detected only, aux.status bit 32), ``num_envs`` (default 1), ``spd_inertia``
     ("stale" = reference quirk Q1 | "fresh"), ``legacy_change_step_bug`` (quirk Q4, default True),
     and ``cfg.robot.xml_path`` (explicit MJCF; default = shipped table for ``humanoid_type``).
     """

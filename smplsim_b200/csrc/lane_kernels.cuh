@@ -42,10 +42,10 @@
 #define L_ST_SELF_CONTACT 32 // SMPLSIM_STATUS_SELF_CONTACT: a geom pair MuJoCo would collide touches (not simulated)
 
 // ------------------------------------------------------------------ compile-time sizes / per-env shared-memory layout (words)
-template <int NB_, int NV_, int NG_, int NS_, int NMBI_, int NMBO_, int NCS_, int NLS_, int RECT_>
+template <int NB_, int NV_, int NG_, int NS_, int NMBI_, int NMBO_, int NCS_, int NLS_, int RECT_, int SELFCOL_ = 0>
 struct LCfg {
   static constexpr int NB = NB_, NV = NV_, NQ = NV_ + 1, NU = NV_ - 6, NG = NG_, NS = NS_, NMBI = NMBI_, NMBO = NMBO_, NCS = NCS_, NLS = NLS_;
-  static constexpr int RECT = RECT_, LPE = LM_LPE, EPW = 32 / LM_LPE;
+  static constexpr int RECT = RECT_, SELFCOL = SELFCOL_, LPE = LM_LPE, EPW = 32 / LM_LPE;   // SELFCOL: geom-geom (two-body) rows compiled in
   static constexpr int BODYW = 24, MBIW = 28, MBOW = 32, CONW = 24, LIMW = 8, RECW = 28, ROOTW = 44;
   static constexpr int r4(int n) { return (n + 3) & ~3; }
   static constexpr int qpos = 0, qvel = qpos + r4(NQ), qacc = qvel + r4(NV), act = qacc + r4(NV), tau = act + r4(NU), qstar = tau + r4(NU),
@@ -61,6 +61,18 @@ struct LCfg {
 #define LMI_NCON 0
 #define LMI_NLIM 1
 #define LMI_DISP 2   // root displacement x, y accumulated over the substeps of this call (words 2, 3)
+#define LMI_NSELF 4  // geom-geom contacts of this substep (two list entries each, starting at LMI_SELF0)
+#define LMI_SELF0 5
+#define L_MAXSELF 4   // simultaneous geom-geom contacts simulated per env (16 two-body rows, two per lane); more are dropped with L_ST_ROWS_DROPPED
+#define L_SELFQ (L_MAXSELF / 2)   // two-body rows per lane: lane li owns rows li, li + 8, ...
+#define LCE_SELF 64   // info bit: entry A of a geom-geom contact (entry B follows: [0 | n 3 | b1 | b2 | - - | lam 4 | part1 4 | part2 4 | r0 4])
+#define LSB_N 1
+#define LSB_B1 4
+#define LSB_B2 5
+#define LSB_LAM 8
+#define LSB_P1 12
+#define LSB_P2 16
+#define LSB_R0 20
 // task words (as in round 1)
 #define L_TSK_CHANGE 4
 #define L_TSK_CURT 5
@@ -100,6 +112,7 @@ struct LLane {
   int env;
   unsigned tm;     // tensor-memory address of this warp's record block (RECT = 1)
   float* gscr;     // overflow contact entries of this env (global scratch)
+  float* gbody;    // body quaternion (4) + spatial velocity about the root origin (6) of the current forward pass [10 nb] (self-collision; NULL: off)
   int* gpfl;       // working set per contact slot carried across launches (handle-internal scratch, r4(NS / 4) words per env)
   float* gsens;    // framelinvel / frameangvel of the last forward pass [6 nb] of this env (global scratch; NULL: not wanted)
 };
@@ -459,6 +472,11 @@ __device__ __forceinline__ S6 l_body_post(const LBody& lb, float* sm, const LLan
     }
   }
   if (flags & LF_XQUAT) ((float4*)(sm + C::xq))[b] = make_float4(P.q.w, P.q.x, P.q.y, P.q.z);
+  if (C::SELFCOL && (flags & LF_COLLIDE) && w.gbody) {     // pose / velocity of every body for the geom-geom narrow phase that follows the sweep
+    float* gb = w.gbody + 10 * b;
+    gb[0] = P.q.w; gb[1] = P.q.x; gb[2] = P.q.y; gb[3] = P.q.z;
+    st6(gb + 4, P.v);
+  }
   return pbv;
 }
 
@@ -752,7 +770,7 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
   }
   LFkOut o;
   if (flags & LF_COLLIDE) {
-    if (w.live && w.li == 0) { ((int*)sm)[C::misc + LMI_NCON] = ncon; ((int*)sm)[C::misc + LMI_NLIM] = min(nlim, C::NLS); }
+    if (w.live && w.li == 0) { ((int*)sm)[C::misc + LMI_NCON] = ncon; ((int*)sm)[C::misc + LMI_NLIM] = min(nlim, C::NLS); ((int*)sm)[C::misc + LMI_NSELF] = 0; }
     unsigned lo = (unsigned)(gbits & 0xffffffffull), hi = (unsigned)(gbits >> 32);
 #pragma unroll
     for (int of = LM_LPE / 2; of > 0; of >>= 1) {
@@ -815,6 +833,173 @@ __device__ __forceinline__ void l_fold_contacts(const LHdr& H, float* sm, const 
   }
 }
 
+// closest points of the segments c1 + s a1 (|s| <= h1) and c2 + t a2 (|t| <= h2), a1, a2 unit: clamped solution
+__device__ __forceinline__ void l_segment_segment(V3 c1, V3 a1, float h1, V3 c2, V3 a2, float h2, float* so, float* to) {
+  V3 r = c1 - c2;
+  float b = dot(a1, a2), cc = dot(a1, r), f = dot(a2, r), den = 1.0f - b * b;
+  float s = (den > 1e-6f) ? (b * f - cc) / den : 0.f;
+  s = fminf(fmaxf(s, -h1), h1);
+  float t = b * s + f;
+  if (t > h2) { t = h2; s = fminf(fmaxf(b * t - cc, -h1), h1); }
+  else if (t < -h2) { t = -h2; s = fminf(fmaxf(b * t - cc, -h1), h1); }
+  *so = s; *to = t;
+}
+
+
+// ------------------------------------------------------------------ geom-geom contacts (self-collision): two-body rows
+// A contact between bodies b1, b2 has J a = x . (a_b2 - a_b1): it cannot be folded into one body's articulated inertia.  Its rows live
+// in the same list as the floor rows (entry A: point, tangent, D, aref, phi, r, rs; entry B: normal, bodies, multipliers, partial
+// row values) and enter the ABA passes as EXTERNAL wrenches lam_k x_k (+ on b2, - on b1); l_linsolve finds the multipliers of the
+// active rows by Woodbury on top of the factors of the current working set.
+template <class C>
+__device__ __forceinline__ bool l_self_touches(const float* sm, const LLane& w, int b) {
+  const int ns = ((const int*)sm)[C::misc + LMI_NSELF];
+  bool t = false;
+  for (int s = 0; s < ns; s++) {
+    const int* eb = (const int*)l_centry<C>((float*)sm, w, ((const int*)sm)[C::misc + LMI_SELF0] + 2 * s + 1);
+    t = t || eb[LSB_B1] == b || eb[LSB_B2] == b;
+  }
+  return t;
+}
+// bias force of body b -= external wrench of the geom-geom rows: f = sum_k lam_k d_k at cp, + on b2, - on b1
+template <class C>
+__device__ __forceinline__ void l_self_wrench(const LHdr& H, float* sm, const LLane& w, int b, S6& p) {
+  const int ns = ((const int*)sm)[C::misc + LMI_NSELF];
+  for (int s = 0; s < ns; s++) {
+    const int c0 = ((const int*)sm)[C::misc + LMI_SELF0] + 2 * s;
+    const float* ea = l_centry<C>(sm, w, c0); const float* eb = l_centry<C>(sm, w, c0 + 1);
+    const int b1 = ((const int*)eb)[LSB_B1], b2 = ((const int*)eb)[LSB_B2];
+    if (b != b1 && b != b2) continue;
+    const V3 n = ld3(eb + LSB_N), t1 = ld3(ea + LCE_T1), t2 = cross(n, t1), cp = ld3(ea + LCE_CP);
+    V3 f = v3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; k++) f = f + eb[LSB_LAM + k] * l_pyr_dir(H, n, t1, t2, k);
+    if (b == b1) f = -1.0f * f;
+    p.l = p.l - f; p.a = p.a - cross(cp, f);
+  }
+}
+// partial row values x_k . a_b of the geom-geom rows that touch body b (part1 for b1, part2 for b2)
+template <class C>
+__device__ __forceinline__ void l_self_part(const LHdr& H, float* sm, const LLane& w, int b, S6 a) {
+  const int ns = ((const int*)sm)[C::misc + LMI_NSELF];
+  for (int s = 0; s < ns; s++) {
+    const int c0 = ((const int*)sm)[C::misc + LMI_SELF0] + 2 * s;
+    const float* ea = l_centry<C>(sm, w, c0); float* eb = l_centry<C>(sm, w, c0 + 1);
+    const int b1 = ((const int*)eb)[LSB_B1], b2 = ((const int*)eb)[LSB_B2];
+    if (b != b1 && b != b2) continue;
+    const V3 n = ld3(eb + LSB_N), t1 = ld3(ea + LCE_T1), t2 = cross(n, t1), cp = ld3(ea + LCE_CP);
+    const V3 ac = a.l + cross(a.a, cp);
+#pragma unroll
+    for (int k = 0; k < 4; k++) eb[(b == b2 ? LSB_P2 : LSB_P1) + k] = dot(l_pyr_dir(H, n, t1, t2, k), ac);
+  }
+}
+// rows li + 8 q of the env's geom-geom rows (row = 4 * contact + k): rs = part2 - part1 - aref into entry A; rs[q] (0 without a row)
+template <class C>
+__device__ __forceinline__ void l_self_fix(float* sm, const LLane& w, bool on, float* rs) {
+#pragma unroll
+  for (int q = 0; q < L_SELFQ; q++) {
+    rs[q] = 0.f;
+    if (on) {
+      const int ns = ((const int*)sm)[C::misc + LMI_NSELF], r = w.li + LM_LPE * q, s = r >> 2, k = r & 3;
+      if (s < ns) {
+        const int c0 = ((const int*)sm)[C::misc + LMI_SELF0] + 2 * s;
+        float* ea = l_centry<C>(sm, w, c0); const float* eb = l_centry<C>(sm, w, c0 + 1);
+        rs[q] = eb[LSB_P2 + k] - eb[LSB_P1 + k] - ea[LCE_AREF + k];
+        ea[LCE_RS + k] = rs[q];
+      }
+    }
+  }
+}
+
+// geom-geom narrow phase on the poses / velocities the outward sweep left in the body scratch: capsule / sphere pairs that pass
+// MuJoCo's filters (LPair list), one contact at the closest points, normal from geom1 to geom2, position midway in the overlap,
+// default tangent (mju_makeFrame); impedance / R / aref as for the floor rows with tran = invweight0(b1) + invweight0(b2).
+// Returns the number of contacts of this lane's env; *dropped: more than L_MAXSELF touched.
+template <class C>
+__device__ __noinline__ int l_self_collide(const float* ms, float* sm, const LLane& w, int* dropped) {
+  const LHdr& H = l_hdr<C>(ms);
+  const LBody* MB = l_bodies(ms);
+  const LGeom* MG = l_geoms(ms);
+  const LPair* PR = (const LPair*)((const char*)ms + H.pair_off);
+  const int ncon = ((const int*)sm)[C::misc + LMI_NCON];
+  int nself = 0;
+  for (int base = 0; base < H.npair; base += LM_LPE) {
+    const int i = base + w.li;
+    bool hit = false;
+    V3 n = v3(1.f, 0.f, 0.f), pos = n; float dist = 0.f; int g1 = 0, g2 = 0;
+    if (w.live && i < H.npair) {
+      g1 = PR[i].g1; g2 = PR[i].g2;
+      const LGeom& G1 = MG[g1]; const LGeom& G2 = MG[g2];
+      const V3 x1 = ld3(sm + C::body + C::BODYW * G1.body + LBR_X), x2 = ld3(sm + C::body + C::BODYW * G2.body + LBR_X);
+      const float r1 = G1.size[0], r2 = G2.size[0];
+      const float h1 = (G1.type == SMPLSIM_GEOM_CAPSULE) ? G1.size[1] : 0.f, h2 = (G2.type == SMPLSIM_GEOM_CAPSULE) ? G2.size[1] : 0.f;
+      const V3 dx = x2 - x1;
+      const float reach = h1 + h2 + r1 + r2 + H.margin + sqrtf(dot(ld3(G1.pos), ld3(G1.pos))) + sqrtf(dot(ld3(G2.pos), ld3(G2.pos)));
+      if (dot(dx, dx) <= reach * reach) {      // body origins close enough: read the orientations
+        const float* q1 = w.gbody + 10 * G1.body; const float* q2 = w.gbody + 10 * G2.body;
+        Q4 a; a.w = q1[0]; a.x = q1[1]; a.y = q1[2]; a.z = q1[3];
+        Q4 b; b.w = q2[0]; b.x = q2[1]; b.y = q2[2]; b.z = q2[3];
+        const V3 c1 = x1 + qrot(a, ld3(G1.pos)), c2 = x2 + qrot(b, ld3(G2.pos));
+        const V3 dc = c2 - c1;
+        const float rc = h1 + h2 + r1 + r2 + H.margin;
+        if (dot(dc, dc) <= rc * rc) {
+          const V3 a1 = qrot(a, v3(G1.mat[2], G1.mat[5], G1.mat[8])), a2 = qrot(b, v3(G2.mat[2], G2.mat[5], G2.mat[8]));
+          float sp, tp;
+          l_segment_segment(c1, a1, h1, c2, a2, h2, &sp, &tp);
+          const V3 p1 = c1 + sp * a1, p2 = c2 + tp * a2;
+          V3 d = p2 - p1;
+          const float len = sqrtf(dot(d, d));
+          dist = len - r1 - r2;
+          if (dist <= H.margin) {
+            hit = true;
+            n = (len < 1e-15f) ? v3(1.f, 0.f, 0.f) : (1.0f / len) * d;
+            pos = p1 + (r1 + 0.5f * dist) * n;
+          }
+        }
+      }
+    }
+    const unsigned bal = (__ballot_sync(L_FULL, hit) & w.gmask) >> w.gbase;
+    const int idx = nself + __popc(bal & ((1u << w.li) - 1u));
+    if (hit && idx < L_MAXSELF) {
+      const int c0 = ncon + 2 * idx;
+      float* ea = l_centry<C>(sm, w, c0); float* eb = l_centry<C>(sm, w, c0 + 1);
+      const int b1 = MG[g1].body, b2 = MG[g2].body;
+      V3 t1 = (n.y < 0.5f && n.y > -0.5f) ? v3(0.f, 1.f, 0.f) : v3(0.f, 0.f, 1.f);   // mju_makeFrame without a hint
+      t1 = t1 - dot(n, t1) * n;
+      { float nn = sqrtf(dot(t1, t1)); t1 = (nn < 1e-15f) ? v3(1.f, 0.f, 0.f) : (1.0f / nn) * t1; }
+      const V3 t2 = cross(n, t1);
+      const float pm = dist - H.margin, imp = l_impedance(H, pm);
+      const float tran = MB[b1].tiw0 + MB[b2].tiw0;
+      const float R0 = fmaxf((1.f - imp) / imp * (tran + H.mu * H.mu * tran), 1e-15f);
+      const float R1 = R0 / fmaxf(H.impratio, 1e-15f), mu = H.mu * sqrtf(R1 / R0);
+      const S6 v1 = ld6(w.gbody + 10 * b1 + 4), v2 = ld6(w.gbody + 10 * b2 + 4);
+      const V3 vc = (v2.l + cross(v2.a, pos)) - (v1.l + cross(v1.a, pos));
+      ((int*)ea)[LCE_INFO] = 1 | 30 | 32 | LCE_SELF | (g2 << 8);
+      st3(ea + LCE_CP, pos); st3(ea + LCE_T1, t1);
+      ea[LCE_D] = 1.0f / (2.f * mu * mu * R0);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        ea[LCE_AREF + k] = -H.B * dot(l_pyr_dir(H, n, t1, t2, k), vc) - H.K * imp * pm;
+        ea[LCE_PHI + k] = 0.f; ea[LCE_R + k] = 0.f; ea[LCE_RS + k] = 0.f;
+        eb[LSB_LAM + k] = 0.f; eb[LSB_P1 + k] = 0.f; eb[LSB_P2 + k] = 0.f; eb[LSB_R0 + k] = 0.f;
+      }
+      ((int*)eb)[LCE_INFO] = 0;
+      st3(eb + LSB_N, n);
+      ((int*)eb)[LSB_B1] = b1; ((int*)eb)[LSB_B2] = b2;
+    }
+    nself += __popc(bal);
+  }
+  *dropped = nself > L_MAXSELF;
+  nself = min(nself, L_MAXSELF);
+  __syncwarp();
+  if (w.live && w.li == 0) {
+    ((int*)sm)[C::misc + LMI_NSELF] = nself; ((int*)sm)[C::misc + LMI_SELF0] = ncon;
+    ((int*)sm)[C::misc + LMI_NCON] = ncon + 2 * nself;
+  }
+  __syncwarp();
+  return nself;
+}
+
 // root body of the inward sweep (every lane makes the call; lane 0 of the group works): children arrive through the
 // in-mailboxes; (semi-implicit Euler of the free joint, then) elimination of its six dofs; the factors K (6 x 6), c (6) stay in
 // shared memory.  Returns "the root has constraint rows in its subtree".
@@ -835,6 +1020,7 @@ __device__ __noinline__ bool l_root_in(const float* ms, float* sm, const LLane& 
       const int cn = (ci >> 8) & 255;
       dirty = dirty || cn > 0;
       l_fold_contacts<C>(H, sm, w, ci & 255, cn, A, p);
+      if (C::SELFCOL && ((const int*)sm)[C::misc + LMI_NSELF]) { l_self_wrench<C>(H, sm, w, 0, p); dirty = dirty || l_self_touches<C>(sm, w, 0); }
     }
     if (flags & LI_INTEGRATE) {
       float* qpos = sm + C::qpos; float* qvel = sm + C::qvel; const float* qacc = sm + C::qacc;
@@ -930,6 +1116,7 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
         const int cb = ci & 255, cn = (ci >> 8) & 255, lbs = (ci >> 16) & 255, ln = (ci >> 24) & 255;
         dirty = dirty || cn > 0 || ln > 0;
         l_fold_contacts<C>(H, sm, w, cb, cn, A, p);
+        if (C::SELFCOL && ((const int*)sm)[C::misc + LMI_NSELF]) { l_self_wrench<C>(H, sm, w, b, p); dirty = dirty || l_self_touches<C>(sm, w, b); }
         for (int e = lbs; e < lbs + ln; e++) {   // joint-limit rows of this body that sit in the working set
           const float4* l4 = (const float4*)(sm + C::lim + C::LIMW * e);
           float4 u = l4[0], v = l4[1];
@@ -1009,6 +1196,7 @@ __device__ __noinline__ void l_root_acc(const float* ms, float* sm, const LLane&
     l_mbo_put_acc(sm + C::mbo + C::MBOW * lb.out_mbox, a);
     const int ci = ((const int*)br)[LBR_CI];
     *same = l_rows_eval<C>(H, sm, w, ci & 255, (ci >> 8) & 255, a) && *same;
+    if (C::SELFCOL && ((const int*)sm)[C::misc + LMI_NSELF]) l_self_part<C>(H, sm, w, 0, a);
   }
   __syncwarp();
 }
@@ -1054,6 +1242,7 @@ __device__ __noinline__ bool l_sweep_acc(const float* ms, float* sm, const LLane
       if (lb.out_mbox >= 0) l_mbo_put_acc(sm + C::mbo + C::MBOW * lb.out_mbox, a);
       const int ci = ((const int*)br)[LBR_CI], cb = ci & 255, cn = (ci >> 8) & 255, lbs = (ci >> 16) & 255, ln = (ci >> 24) & 255;
       if (cn) same = l_rows_eval<C>(H, sm, w, cb, cn, a) && same;
+      if (C::SELFCOL && ((const int*)sm)[C::misc + LMI_NSELF]) l_self_part<C>(H, sm, w, b, a);
       for (int e = lbs; e < lbs + ln; e++) {
         float* le = sm + C::lim + C::LIMW * e;
         int k = ((const int*)le)[LLE_DOF] - lb.dofadr;
@@ -1132,14 +1321,146 @@ __device__ int g_lstats[32];
 #define L_STAT(i, v) do { } while (0)
 #endif
 
+// ------------------------------------------------------------------ one Newton system of the active-set solve
+// = ABA factors + accelerations for the current working set.  Envs with geom-geom rows (two-body rows cannot be folded into the
+// articulated inertias) get them by Woodbury on top of those factors: with lam the multipliers of the active two-body rows,
+// a(lam) = a(0) + M~^-1 Y lam is affine, so one probe solve per active row gives H = Y^T M~^-1 Y column by column (rows of H live in
+// the lanes: lane i of the env owns row i), (H + D^-1) lam = -r(0) is solved across the 8 lanes, and a last solve applies lam.
+// Returns "sign pattern of all rows == working set" at the resulting point.
+template <class C>
+__device__ __noinline__ bool l_linsolve(const float* ms, float* sm, const LLane& w, bool run, int inflags, bool to_qstar, bool first, LSolveLane& st) {
+  const LHdr& H = l_hdr<C>(ms);
+  if (!C::SELFCOL) {   // no geom-geom rows compiled in: the plain ABA pair
+    l_sweep_in<C>(ms, sm, w, run, inflags, st);
+    return l_sweep_acc<C>(ms, sm, w, run, to_qstar, first, st);
+  }
+  const bool hs = run && H.cfg.self_collision && ((const int*)sm)[C::misc + LMI_NSELF] > 0;
+  const bool anyhs = __any_sync(L_FULL, hs);
+  constexpr int NR = 4 * L_MAXSELF;                 // two-body rows per env; lane li owns rows li + 8 q
+  bool valid[L_SELFQ]; float* ea[L_SELFQ]; float* eb[L_SELFQ]; int krow[L_SELFQ];
+#pragma unroll
+  for (int q = 0; q < L_SELFQ; q++) {
+    const int r = w.li + LM_LPE * q;
+    krow[q] = r & 3;
+    valid[q] = hs && (r >> 2) < ((const int*)sm)[C::misc + LMI_NSELF];
+    ea[q] = sm; eb[q] = sm;
+    if (valid[q]) {
+      const int c0 = ((const int*)sm)[C::misc + LMI_SELF0] + 2 * (r >> 2);
+      ea[q] = l_centry<C>(sm, w, c0); eb[q] = l_centry<C>(sm, w, c0 + 1);
+      eb[q][LSB_LAM + krow[q]] = 0.f;
+    }
+  }
+  if (anyhs) __syncwarp();
+  l_sweep_in<C>(ms, sm, w, run, inflags, st);
+  bool same = l_sweep_acc<C>(ms, sm, w, run, to_qstar, first, st);
+  if (!anyhs) return same;
+  const int rflags = H.dirtypath ? LI_RESWEEP : 0;
+  float r0[L_SELFQ], Dr[L_SELFQ], pscale[L_SELFQ];
+  bool act[L_SELFQ];
+  l_self_fix<C>(sm, w, hs, r0);
+  float Hrow[L_SELFQ][NR];
+#pragma unroll
+  for (int q = 0; q < L_SELFQ; q++) {
+    act[q] = valid[q] && ((((const int*)ea[q])[LCE_INFO] >> (1 + krow[q])) & 1);
+    Dr[q] = valid[q] ? ea[q][LCE_D] : 1.f;
+    pscale[q] = fmaxf(fabsf(r0[q]) * Dr[q], 1.0f);      // probe magnitude ~ the multiplier the row would carry alone
+#pragma unroll
+    for (int j = 0; j < NR; j++) Hrow[q][j] = 0.f;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int qj = 0; qj < L_SELFQ; qj++) {
+#pragma unroll 1
+    for (int lj = 0; lj < LM_LPE; lj++) {
+      const int j = lj + LM_LPE * qj;                                        // probed row: owned by lane lj, slot qj
+      const int actj_ = __shfl_sync(L_FULL, act[qj] ? 1 : 0, w.gbase + lj);  // (collectives never behind a short-circuit)
+      const float Pj = __shfl_sync(L_FULL, pscale[qj], w.gbase + lj);
+      const bool prb = hs && actj_ != 0;
+      if (!__any_sync(L_FULL, prb)) continue;
+      if (prb && w.li == lj) eb[qj][LSB_LAM + krow[qj]] = Pj;
+      __syncwarp();
+      l_sweep_in<C>(ms, sm, w, prb, rflags, st);
+      l_sweep_acc<C>(ms, sm, w, prb, to_qstar, false, st);
+      float v[L_SELFQ];
+      l_self_fix<C>(sm, w, prb, v);
+#pragma unroll
+      for (int q = 0; q < L_SELFQ; q++) {
+        if (prb && valid[q]) {
+          const float hij = (v[q] - r0[q]) / Pj;
+#pragma unroll
+          for (int jj = 0; jj < NR; jj++) if (jj == j) Hrow[q][jj] = hij;
+        }
+      }
+      if (prb && w.li == lj) eb[qj][LSB_LAM + krow[qj]] = 0.f;
+      __syncwarp();
+    }
+  }
+  // (H + D^-1) lam = -r0 on the active rows (identity elsewhere): Gauss-Jordan across the lanes of the env, L_SELFQ rows per lane
+  float Mr[L_SELFQ][NR], rhs[L_SELFQ];
+#pragma unroll
+  for (int qj = 0; qj < L_SELFQ; qj++)
+#pragma unroll
+    for (int lj = 0; lj < LM_LPE; lj++) {
+      const int j = lj + LM_LPE * qj;
+      const bool actj = __shfl_sync(L_FULL, act[qj] ? 1 : 0, w.gbase + lj) != 0;
+#pragma unroll
+      for (int q = 0; q < L_SELFQ; q++) {
+        Mr[q][j] = (act[q] && actj) ? Hrow[q][j] : 0.f;
+        if (q == qj && lj == w.li) Mr[q][j] = act[q] ? Mr[q][j] + 1.0f / Dr[q] : 1.0f;
+      }
+    }
+#pragma unroll
+  for (int q = 0; q < L_SELFQ; q++) rhs[q] = act[q] ? -r0[q] : 0.f;
+#pragma unroll
+  for (int qp = 0; qp < L_SELFQ; qp++)
+#pragma unroll 1
+    for (int lp = 0; lp < LM_LPE; lp++) {
+      const int pp = lp + LM_LPE * qp;          // pivot row: lane lp, slot qp
+      float prow[NR];
+#pragma unroll
+      for (int c = 0; c < NR; c++) prow[c] = __shfl_sync(L_FULL, Mr[qp][c], w.gbase + lp);
+      const float prhs = __shfl_sync(L_FULL, rhs[qp], w.gbase + lp);
+      float piv = 1.f;
+#pragma unroll
+      for (int c = 0; c < NR; c++) if (c == pp) piv = prow[c];
+#pragma unroll
+      for (int q = 0; q < L_SELFQ; q++) {
+        float mp = 0.f;
+#pragma unroll
+        for (int c = 0; c < NR; c++) if (c == pp) mp = Mr[q][c];
+        const float f = (w.li == lp && q == qp) ? 0.f : mp / piv;
+#pragma unroll
+        for (int c = 0; c < NR; c++) Mr[q][c] = fmaf(-f, prow[c], Mr[q][c]);
+        rhs[q] = fmaf(-f, prhs, rhs[q]);
+      }
+    }
+#pragma unroll
+  for (int q = 0; q < L_SELFQ; q++) {
+    float d = 1.f;
+#pragma unroll
+    for (int c = 0; c < NR; c++) if (c == w.li + LM_LPE * q) d = Mr[q][c];
+    if (valid[q]) eb[q][LSB_LAM + krow[q]] = act[q] ? rhs[q] / d : 0.f;
+  }
+  __syncwarp();
+  l_sweep_in<C>(ms, sm, w, hs, rflags, st);
+  const bool same2 = l_sweep_acc<C>(ms, sm, w, hs, to_qstar, false, st);
+  float rsf[L_SELFQ];
+  l_self_fix<C>(sm, w, hs, rsf);
+  bool okrow = true;
+#pragma unroll
+  for (int q = 0; q < L_SELFQ; q++) okrow = okrow && (!valid[q] || ((rsf[q] < 0.f) == act[q]));
+  const bool sameself = l_gall(okrow, w);
+  __syncwarp();
+  return hs ? (same2 && sameself) : same;
+}
+
 // ------------------------------------------------------------------ constraint solve: active-set Newton, every system one ABA pass
 // Returns the number of extra solves; *hit_max: stopped at L_SOLVER_MAXITER.
 template <class C>
 __device__ __noinline__ int l_solve(const float* ms, float* sm, const LLane& w, bool any_rows, LSolveLane& st, bool* hit_max) {
   const LHdr& H = l_hdr<C>(ms);
   // first pass for every live env: the working set inherited from the previous substep is already in the row lists
-  l_sweep_in<C>(ms, sm, w, w.live, 0, st);
-  bool same0 = l_sweep_acc<C>(ms, sm, w, w.live, false, true, st);   // qdd -> qacc
+  bool same0 = l_linsolve<C>(ms, sm, w, w.live, 0, false, true, st);   // qdd -> qacc
   bool run = w.live && any_rows && !same0;
   *hit_max = false;
 #ifdef SMPLSIM_STATS
@@ -1178,8 +1499,7 @@ __device__ __noinline__ int l_solve(const float* ms, float* sm, const LLane& w, 
   int it = 1, iters = 0;
   for (; it < L_SOLVER_MAXITER; it++) {
     if (!(cu ? (__syncthreads_or(run) != 0) : __any_sync(L_FULL, run))) break;
-    l_sweep_in<C>(ms, sm, w, run, H.dirtypath ? LI_RESWEEP : 0, st);
-    bool same = l_sweep_acc<C>(ms, sm, w, run, true, false, st);      // qdd -> qstar
+    bool same = l_linsolve<C>(ms, sm, w, run, H.dirtypath ? LI_RESWEEP : 0, true, false, st);      // qdd -> qstar
     bool fin = run && same, lsrch = run && !same;
     if (__any_sync(L_FULL, lsrch)) {   // exact line search between the iterate (qacc, r, phi) and the trial point (qstar, rs), row space only
       l_rows<C>(sm, w, lsrch, 1, 0.f, o4);
@@ -1345,7 +1665,7 @@ __device__ __forceinline__ void l_save_working_set(const float* ms, float* sm, c
     const int ncon = ((const int*)sm)[C::misc + LMI_NCON];
     for (int c = w.li; c < ncon; c += LM_LPE) {
       int info = ((const int*)l_centry<C>(sm, w, c))[LCE_INFO];
-      if (info & 1) pf[(info >> 16) & 255] = (unsigned char)(info & 31);
+      if ((info & 1) && !(info & LCE_SELF)) pf[(info >> 16) & 255] = (unsigned char)(info & 31);
     }
   }
   __syncwarp();
@@ -1382,6 +1702,11 @@ __device__ __noinline__ void l_substeps(const float* ms, float* sm, const LLane&
     const bool last = (s == nsub - 1);
     int f1 = LF_FK | LF_VEL | LF_COLLIDE | ((spd && stale) ? LF_GOUT : 0) | (last ? LF_SENS : 0);
     LFkOut fk = l_sweep_out<C>(ms, sm, w, f1, bad != 0);
+    if (C::SELFCOL && H.cfg.self_collision && w.gbody && H.npair > 0) {
+      int dr = 0;
+      fk.nrows += 4 * l_self_collide<C>(ms, sm, w, &dr);
+      fk.dropped |= dr;
+    }
     bool hit = false;
     fo->mask = fk.mask;
     if (H.align & 2) __syncthreads();
@@ -1393,6 +1718,7 @@ __device__ __noinline__ void l_substeps(const float* ms, float* sm, const LLane&
       w2.live = w.live && badacc != 0;
       w2.bar = false;
       LFkOut fk2 = l_sweep_out<C>(ms, sm, w2, LF_FK | LF_VEL | LF_COLLIDE | (last ? LF_SENS : 0), false);
+      if (C::SELFCOL && H.cfg.self_collision && w.gbody && H.npair > 0) { int dr = 0; fk2.nrows += 4 * l_self_collide<C>(ms, sm, w2, &dr); }
       bool hit2 = false;
       int it2 = l_solve<C>(ms, sm, w2, fk2.nrows > 0, st, &hit2);
       if (badacc) { fo->mask = fk2.mask; fo->iters = it2; }
@@ -1426,6 +1752,7 @@ struct LStepArgs {
   uint8_t* truncated;
   float* gscr;       // [n, (NS - NCS) * CONW] overflow contact entries
   float* gsens;      // [n, 6 nb] or NULL
+  float* gbody;      // [n, 10 nb] or NULL (self-collision)
   int* gpfl;         // [n, r4(NS / 4)] working set per contact slot
   int n, nsub, mode;
 };
@@ -1438,6 +1765,7 @@ struct LResetArgs {
   float* obs;
   float* gscr;
   float* gsens;
+  float* gbody;
   int* gpfl;
   int n, init_mode;
 };
@@ -1584,18 +1912,6 @@ __device__ __noinline__ void l_write_aux(const float* ms, float* sm, const LLane
   }
 }
 
-// closest points of the segments c1 + s a1 (|s| <= h1) and c2 + t a2 (|t| <= h2), a1, a2 unit: clamped solution
-__device__ __forceinline__ void l_segment_segment(V3 c1, V3 a1, float h1, V3 c2, V3 a2, float h2, float* so, float* to) {
-  V3 r = c1 - c2;
-  float b = dot(a1, a2), cc = dot(a1, r), f = dot(a2, r), den = 1.0f - b * b;
-  float s = (den > 1e-6f) ? (b * f - cc) / den : 0.f;
-  s = fminf(fmaxf(s, -h1), h1);
-  float t = b * s + f;
-  if (t > h2) { t = h2; s = fminf(fmaxf(b * t - cc, -h1), h1); }
-  else if (t < -h2) { t = -h2; s = fminf(fmaxf(b * t - cc, -h1), h1); }
-  *so = s; *to = t;
-}
-
 // Self-collision is not simulated.  Once per env step, on the final kinematics (xquat staging + body rows), test the
 // capsule / sphere geom pairs MuJoCo's filters let through (smpl_humanoid.xml:5,24,231-242); a touching pair means the reference
 // would have generated a geom-geom contact here.  Returns true for this lane's env.
@@ -1637,7 +1953,7 @@ extern __shared__ float4 l_smem4[];
 
 // CTA prologue: stage the constant table, carve the env rows, claim tensor memory.  Shared memory: [table | 4 words | env rows]
 template <class C>
-__device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int img_bytes, LLane& w, const float*& ms, int n, float* gscr, float* gsens, int* gpfl) {
+__device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int img_bytes, LLane& w, const float*& ms, int n, float* gscr, float* gsens, int* gpfl, float* gbody = nullptr) {
   float* smem = L_SMEM;
   unsigned* slot = (unsigned*)(smem + img_bytes / 4);   // [0] tensor-memory base, [2..3] mbarrier of the table copy
 #ifndef SMPLSIM_EMU
@@ -1696,6 +2012,7 @@ __device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int im
   // tensor memory: a warp reaches the 32 lanes of its quarter (warp id mod 4); warps 4.. take the upper 256 columns
   w.tm = tbase + ((unsigned)((wib & 3) * 32) << 16) + (unsigned)((wib >> 2) * 256);
   w.gscr = gscr + (size_t)(w.live ? w.env : 0) * (size_t)(C::CONW * (C::NS - C::NCS));
+  w.gbody = gbody ? gbody + (size_t)(w.live ? w.env : 0) * (size_t)(10 * C::NB) : nullptr;
   w.gpfl = gpfl ? gpfl + (size_t)(w.live ? w.env : 0) * (size_t)C::PFLW : nullptr;
   w.gsens = gsens ? gsens + (size_t)(w.live ? w.env : 0) * (size_t)(6 * C::NB) : nullptr;
   return smem + img_bytes / 4 + 4 + (size_t)(wib * C::EPW + sub) * C::total;
@@ -1733,12 +2050,12 @@ __device__ __noinline__ void l_spd_prologue(const float* ms, float* sm, const LL
 template <class C>
 __global__ void __launch_bounds__(256, 1) k_step5(const float* __restrict__ gimg, int img_bytes, LStepArgs a) {
   const float* ms; LLane w;
-  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.gscr, a.gsens, a.gpfl);
+  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.gscr, a.gsens, a.gpfl, a.gbody);
   const LHdr& H = l_hdr<C>(ms);
   const size_t eo = w.live ? (size_t)w.env : 0;   // lanes without a live env keep running (predicated): warp collectives stay legal
   const bool spd = (H.cfg.control_mode == SMPLSIM_CTRL_UHC_PD);
   LSolveLane st; st.dirty_bits = 0u; st.rc_bits = 0u;
-  if (w.live && w.li == 0) { sm[C::misc + LMI_DISP] = 0.f; sm[C::misc + LMI_DISP + 1] = 0.f; }
+  if (w.live && w.li == 0) { sm[C::misc + LMI_DISP] = 0.f; sm[C::misc + LMI_DISP + 1] = 0.f; ((int*)sm)[C::misc + LMI_NSELF] = 0; ((int*)sm)[C::misc + LMI_NCON] = 0; ((int*)sm)[C::misc + LMI_NLIM] = 0; }
   if (w.live) for (int i = w.li; i < (H.nslot + 3) / 4; i += LM_LPE) ((int*)sm)[C::pfl + i] = w.gpfl ? w.gpfl[i] : 0;   // working set of the previous call
   l_copy_in<C>(sm + C::act, a.action + eo * H.nu, H.nu, w);
   if (spd && H.cfg.spd_stale && a.mode == 0) l_spd_prologue<C>(ms, sm, w, a.st, st);
@@ -1757,7 +2074,7 @@ __global__ void __launch_bounds__(256, 1) k_step5(const float* __restrict__ gimg
   LFwd fo; fo.mask = 0ull; fo.iters = 0; fo.status = 0;
   l_substeps<C>(ms, sm, w, a.nsub, a.mode, &fo, a.st, true, false, st);
   l_sweep_out<C>(ms, sm, w, LF_FK | LF_XQUAT, false);
-  if (H.npair > 0 && a.aux.status && l_self_contact<C>(ms, sm, w)) fo.status |= L_ST_SELF_CONTACT;
+  if (H.npair > 0 && !H.cfg.self_collision && a.aux.status && l_self_contact<C>(ms, sm, w)) fo.status |= L_ST_SELF_CONTACT;   // detected, not simulated
   if (a.mode == 0) {
     int* ti = (int*)(sm + C::tsk);
     if (w.live && w.li == 0) ti[L_TSK_CURT] += 1;
@@ -1796,14 +2113,14 @@ __global__ void __launch_bounds__(256, 1) k_step5(const float* __restrict__ gimg
 template <class C>
 __global__ void __launch_bounds__(256, 1) k_reset5(const float* __restrict__ gimg, int img_bytes, LResetArgs a) {
   const float* ms; LLane w;
-  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.gscr, a.gsens, a.gpfl);
+  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.gscr, a.gsens, a.gpfl, a.gbody);
   const LHdr& H = l_hdr<C>(ms);
   if (w.live && a.mask && !a.mask[w.env]) w.live = false;
   size_t eo = w.live ? (size_t)w.env : 0;
   const SmplsimEnvCfg& c = H.cfg;
   int init = a.init_mode < 0 ? c.state_init : a.init_mode;
   LSolveLane st; st.dirty_bits = 0u; st.rc_bits = 0u;
-  if (w.live && w.li == 0) { sm[C::misc + LMI_DISP] = 0.f; sm[C::misc + LMI_DISP + 1] = 0.f; }
+  if (w.live && w.li == 0) { sm[C::misc + LMI_DISP] = 0.f; sm[C::misc + LMI_DISP + 1] = 0.f; ((int*)sm)[C::misc + LMI_NSELF] = 0; ((int*)sm)[C::misc + LMI_NCON] = 0; ((int*)sm)[C::misc + LMI_NLIM] = 0; }
   l_task_io<C>(sm, w, a.st, false);
   if (w.live && w.li == 0) {
     int* ti = (int*)(sm + C::tsk);

@@ -18,9 +18,9 @@
 #endif
 
 // model classes the kernels are instantiated for: <bodies, dofs, geoms, contact slots, in-mailboxes, out-mailboxes, contact
-// entries in shared memory, limit rows, records in tensor memory>
-#define L_SMPL(RECT) LCfg<24, 75, 24, 64, 5, 2, 20, 16, RECT>
-#define L_SMPLX(RECT) LCfg<52, 159, 52, 128, 16, 8, 24, 24, RECT>
+// entries in shared memory, limit rows, records in tensor memory, geom-geom rows compiled in>
+#define L_SMPL(RECT, SC) LCfg<24, 75, 24, 64, 5, 2, 20, 16, RECT, SC>
+#define L_SMPLX(RECT, SC) LCfg<52, 159, 52, 128, 16, 8, 24, 24, RECT, SC>
 
 struct SmplsimHandle {
   LaneImage img;
@@ -28,9 +28,11 @@ struct SmplsimHandle {
   float* gscr = nullptr;   // overflow contact entries
   float* gsens = nullptr;  // body velocities of the last forward pass (obs v2 / aux)
   int* gpfl = nullptr;     // working set per contact slot, carried from call to call (solver warm start only)
+  float* gbody = nullptr;  // body pose / velocity of the current forward pass (self-collision narrow phase)
   int num_envs = 0, device = 0, nsm = 148, max_smem = 0;
   int cls = 0;             // 1 SMPL class, 2 SMPL-X class
   int rect = 1;            // lane records in tensor memory (1) or shared memory (0)
+  int selfcol = 0;         // cfg.env.self_collision: kernels with the geom-geom rows compiled in
   int wpb = 0;             // warps per CTA
   size_t smem = 0, env_words = 0;
 };
@@ -95,15 +97,19 @@ static void run_kin(SmplsimHandle* h, const LKinArgs& a, cudaStream_t st) {
   int wpb = h->wpb, per = wpb * C::EPW;
   L_LAUNCH(k_kin5<C>, (a.n + per - 1) / per, 32 * wpb, h->smem, st, h->dimg, h->img.hdr()->bytes, a);
 }
-// dispatch over (model class, record placement)
-#define L_DISPATCH(h, CALL)                                          \
-  do {                                                               \
-    switch (((h)->cls << 1) | (h)->rect) {                           \
-      case (1 << 1) | 0: { typedef L_SMPL(0) C_; CALL; } break;      \
-      case (1 << 1) | 1: { typedef L_SMPL(1) C_; CALL; } break;      \
-      case (2 << 1) | 0: { typedef L_SMPLX(0) C_; CALL; } break;     \
-      default: { typedef L_SMPLX(1) C_; CALL; } break;               \
-    }                                                                \
+// dispatch over (model class, record placement, self-collision)
+#define L_DISPATCH(h, CALL)                                                   \
+  do {                                                                        \
+    switch (((h)->cls << 2) | ((h)->rect << 1) | (h)->selfcol) {              \
+      case (1 << 2) | 0: { typedef L_SMPL(0, 0) C_; CALL; } break;            \
+      case (1 << 2) | 1: { typedef L_SMPL(0, 1) C_; CALL; } break;            \
+      case (1 << 2) | 2: { typedef L_SMPL(1, 0) C_; CALL; } break;            \
+      case (1 << 2) | 3: { typedef L_SMPL(1, 1) C_; CALL; } break;            \
+      case (2 << 2) | 0: { typedef L_SMPLX(0, 0) C_; CALL; } break;           \
+      case (2 << 2) | 1: { typedef L_SMPLX(0, 1) C_; CALL; } break;           \
+      case (2 << 2) | 2: { typedef L_SMPLX(1, 0) C_; CALL; } break;           \
+      default: { typedef L_SMPLX(1, 1) C_; CALL; } break;                     \
+    }                                                                         \
   } while (0)
 
 extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cfg, int num_envs, int cuda_device, SmplsimHandle** out) {
@@ -120,7 +126,7 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   { const char* dp = std::getenv("SMPLSIM_DIRTYPATH"); if (dp) H.dirtypath = std::atoi(dp); }
   { const char* al = std::getenv("SMPLSIM_ALIGN"); if (al) H.align = std::atoi(al); }   // CTA phase-alignment barriers (bit 0 substep, 1 solve, 2 stable-PD sweep)
   for (int b = 0; b < H.nb; b++) if (h->img.bodies()[b].ngeom > 1) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "more than one geom on a body"); }
-  typedef L_SMPL(0) CS; typedef L_SMPLX(0) CX;
+  typedef L_SMPL(0, 0) CS; typedef L_SMPLX(0, 0) CX;
   if (H.nb == CS::NB && H.nv == CS::NV && H.ng <= CS::NG && H.nslot <= CS::NS && H.nmbi <= CS::NMBI && H.nmbo <= CS::NMBO) h->cls = 1;
   else if (H.nb == CX::NB && H.nv == CX::NV && H.ng <= CX::NG && H.nslot <= CX::NS && H.nmbi <= CX::NMBI && H.nmbo <= CX::NMBO) h->cls = 2;
   else {
@@ -130,7 +136,7 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
     delete h;
     return fail(SMPLSIM_EUNSUPPORTED, msg);
   }
-  h->num_envs = num_envs; h->device = cuda_device;
+  h->num_envs = num_envs; h->device = cuda_device; h->selfcol = cfg->self_collision ? 1 : 0;
   DeviceGuard guard(cuda_device);
   cudaError_t e = cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cuda_device);
 #ifndef SMPLSIM_EMU
@@ -151,7 +157,8 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   L_DISPATCH(h, pw = (size_t)C_::PFLW);
   if (e == cudaSuccess) e = cudaMalloc(&h->gpfl, pw * num_envs * 4);
   if (e == cudaSuccess) e = cudaMemset(h->gpfl, 0, pw * num_envs * 4);
-  if (e != cudaSuccess) { if (h->dimg) cudaFree(h->dimg); if (h->gscr) cudaFree(h->gscr); if (h->gsens) cudaFree(h->gsens); if (h->gpfl) cudaFree(h->gpfl); delete h; return fail(SMPLSIM_ECUDA, std::string("smplsim_create: ") + cudaGetErrorString(e)); }
+  if (e == cudaSuccess && cfg->self_collision) e = cudaMalloc(&h->gbody, (size_t)10 * H.nb * num_envs * 4);
+  if (e != cudaSuccess) { if (h->dimg) cudaFree(h->dimg); if (h->gscr) cudaFree(h->gscr); if (h->gsens) cudaFree(h->gsens); if (h->gpfl) cudaFree(h->gpfl); if (h->gbody) cudaFree(h->gbody); delete h; return fail(SMPLSIM_ECUDA, std::string("smplsim_create: ") + cudaGetErrorString(e)); }
   *out = h;
   return SMPLSIM_OK;
 }
@@ -163,6 +170,7 @@ extern "C" int smplsim_destroy(SmplsimHandle* h) {
   cudaFree(h->gscr);
   cudaFree(h->gsens);
   cudaFree(h->gpfl);
+  cudaFree(h->gbody);
   delete h;
   return SMPLSIM_OK;
 }
@@ -193,7 +201,7 @@ extern "C" int smplsim_step(SmplsimHandle* h, const SmplsimState* st, const floa
   LStepArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
   a.action = action_dev; a.obs = obs_dev; a.reward = reward_dev; a.terminated = terminated_dev; a.truncated = truncated_dev;
-  a.gscr = h->gscr; a.gpfl = h->gpfl; a.n = h->num_envs; a.nsub = h->img.hdr()->cfg.nsubsteps; a.mode = 0;
+  a.gscr = h->gscr; a.gpfl = h->gpfl; a.gbody = h->gbody; a.n = h->num_envs; a.nsub = h->img.hdr()->cfg.nsubsteps; a.mode = 0;
   a.gsens = want_sens(h, aux) ? h->gsens : nullptr;
   L_DISPATCH(h, run_step<C_>(h, a, (cudaStream_t)stream));
   CUDA_TRY(cudaGetLastError());
@@ -205,7 +213,7 @@ extern "C" int smplsim_mj_step(SmplsimHandle* h, const SmplsimState* st, const f
   DeviceGuard guard(h->device);
   LStepArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
-  a.action = ctrl_dev; a.gscr = h->gscr; a.gpfl = h->gpfl; a.n = h->num_envs; a.nsub = nsub; a.mode = 1;
+  a.action = ctrl_dev; a.gscr = h->gscr; a.gpfl = h->gpfl; a.gbody = h->gbody; a.n = h->num_envs; a.nsub = nsub; a.mode = 1;
   a.gsens = want_sens(h, aux) ? h->gsens : nullptr;
   L_DISPATCH(h, run_step<C_>(h, a, (cudaStream_t)stream));
   CUDA_TRY(cudaGetLastError());
@@ -223,7 +231,7 @@ extern "C" int smplsim_reset(SmplsimHandle* h, const SmplsimState* st, const uin
   DeviceGuard guard(h->device);
   LResetArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
-  a.mask = mask_dev; a.qpos0 = qpos0_dev; a.qvel0 = qvel0_dev; a.obs = obs_dev; a.gscr = h->gscr; a.gpfl = h->gpfl; a.n = h->num_envs; a.init_mode = mode;
+  a.mask = mask_dev; a.qpos0 = qpos0_dev; a.qvel0 = qvel0_dev; a.obs = obs_dev; a.gscr = h->gscr; a.gpfl = h->gpfl; a.gbody = h->gbody; a.n = h->num_envs; a.init_mode = mode;
   a.gsens = want_sens(h, aux) ? h->gsens : nullptr;
   L_DISPATCH(h, run_reset<C_>(h, a, (cudaStream_t)stream));
   CUDA_TRY(cudaGetLastError());

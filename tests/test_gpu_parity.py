@@ -479,3 +479,62 @@ def test_self_contact_flag_matches_mujoco_pair_filters(backend):
         assert bool(st[i] & 32) == bool(selfc.any()), (i, st[i], con["dist"][selfc])
     om.set_self_collision(False)
     assert ncmp >= n - 4 and 3 <= nhit < ncmp, (ncmp, nhit)
+
+
+def test_mj_step_self_contact_states(backend):
+    """cfg.env.self_collision: geom-geom contacts between the capsule / sphere pairs MuJoCo's filters let through are
+    two-body rows; the product solves them by Woodbury on top of the ABA factors, the oracle by a dense Newton.  One substep from
+    fallen / tangled states (Fall-init rollouts of the self-colliding oracle): qpos, qvel norm-relative 1e-4, qacc 5e-4, on at least
+    30 states that do have geom-geom contacts (up to 4 at once = 16 two-body rows; states with more raise status bit 8 and are
+    not compared)."""
+    cfg, om = make_models(env="getup", control_mode="torque", self_collision=True)
+    m = om.model
+    n = 96
+    q, v, w = rollout_states(make_models(env="getup", control_mode="uhc_pd", self_collision=True)[1], n, seed=7, init_mode=1, control_sigma=0.6)
+    rng = np.random.default_rng(2)
+    ctrl = rng.uniform(-60, 60, (n, m.nu))
+    env = backend.batch(cfg, n)
+    env.set_state(backend.t(q), backend.t(v))
+    env.qacc_warm.copy_(backend.t(w))
+    env.mj_step(backend.t(ctrl), 1)
+    gq, gv, ga = env.qpos.cpu().numpy(), env.qvel.cpu().numpy(), env.qacc.cpu().numpy()
+    st = env.status.cpu().numpy()
+    nself_states = ndropped = 0
+    worst = 0.0
+    for i in range(n):
+        e = _oracle_one_step(om, q[i], v[i], w[i], ctrl[i])
+        con = e.contacts()
+        ns = int((con["geom1"] > 0).sum())
+        if e.ncon and (np.abs(con["dist"] - m.margin) < 1e-5).any():
+            continue
+        if ns > 4:
+            assert st[i] & 8, (i, ns, st[i])
+            ndropped += 1
+            continue
+        assert not (st[i] & (8 | 16 | 32)), (i, ns, st[i])
+        nself_states += ns > 0
+        worst = max(worst, relerr(gv[i], e.qvel), relerr(gq[i], e.qpos))
+        assert relerr(gv[i], e.qvel) < TOL and relerr(gq[i], e.qpos) < TOL, (i, ns, e.ncon, relerr(gv[i], e.qvel))
+        assert relerr(ga[i], e.qacc) < 5e-4, (i, ns, relerr(ga[i], e.qacc))
+    print(f"{nself_states} states with geom-geom contacts compared (worst {worst:.2e}); {ndropped} with more than 4 dropped")
+    assert nself_states >= 30 and ndropped <= n // 10
+
+
+def test_env_step_with_self_collision_matches_oracle(backend):
+    """getup env steps (Fall init: 45 substeps of random actions on the floor, then 15 per step) with cfg.env.self_collision on both sides."""
+    cfg, om = make_models(env="getup", seed=11, self_collision=True)
+    m = om.model
+    n = 8
+    env = backend.batch(cfg, n, seed=11)
+    obs0 = env.reset().cpu().numpy().copy()
+    oes = [orc.OracleEnv(om, env_id=i) for i in range(n)]
+    for i, e in enumerate(oes):
+        assert np.abs(obs0[i] - e.reset()).max() < 5e-3, i
+    rng = np.random.default_rng(3)
+    for t in range(2):
+        act = np.clip(rng.normal(size=(n, m.nu)) * 0.2, -1, 1)
+        obs, rew, term, trunc = [x.cpu().numpy() for x in env.step(backend.t(act))]
+        for i, e in enumerate(oes):
+            o, r, te, tr = e.step(act[i])
+            assert np.abs(obs[i] - o).max() < 1e-2 * (t + 1), (t, i, np.abs(obs[i] - o).max())
+            assert bool(term[i]) == te and bool(trunc[i]) == tr

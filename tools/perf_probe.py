@@ -12,7 +12,8 @@ from smplsim_b200.cfg import make_cfg  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 warm = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-env = HumanoidBatchB200(make_cfg(env="speed"), num_envs=n, with_aux=False)
+OV = {"env.self_collision": True} if os.environ.get("SMPLSIM_SELFCOL") else {}
+env = HumanoidBatchB200(make_cfg(env="speed", overrides=OV), num_envs=n, with_aux=False)
 env.reset()
 g = torch.Generator(device="cuda:0"); g.manual_seed(0)
 acts = torch.clamp(torch.randn(warm + 8, n, env.num_actions, generator=g, device="cuda:0") * 0.0821, -1, 1)
@@ -22,7 +23,7 @@ torch.cuda.synchronize(); t0 = time.time()
 for i in range(8):
     env.step(acts[warm + i]); env.reset_done()
 torch.cuda.synchronize(); dt = (time.time() - t0) / 8
-env2 = HumanoidBatchB200(make_cfg(env="speed"), num_envs=min(n, 1024))
+env2 = HumanoidBatchB200(make_cfg(env="speed", overrides=OV), num_envs=min(n, 1024))
 env2.reset()
 its = []
 for i in range(warm + 8):
