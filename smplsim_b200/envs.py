@@ -72,7 +72,7 @@ class HumanoidEnvB200(_EnvBase):
         self.viewer = None
         self.renderer = None
         self.dtype = np.float32
-        self._b = HumanoidBatchB200(cfg, num_envs=1, device=device, seed=int(cfg.get("seed", 0)))
+        self._b = self._make_batch(cfg, device)
         m = self._b.model
         self.control_mode = e.control_mode
         self.max_episode_length = e.episode_length
@@ -97,6 +97,10 @@ class HumanoidEnvB200(_EnvBase):
         self.np_random = np.random.default_rng(int(cfg.get("seed", 0)))
         self.reward_info = {}
 
+    def _make_batch(self, cfg, device):
+        """The num_envs=1 handle behind this env (CUDA; there is no CPU path)."""
+        return HumanoidBatchB200(cfg, num_envs=1, device=device, seed=int(cfg.get("seed", 0)))
+
     # ------------------------------------------------------------------ sizes
     def get_action_size(self):
         return self._b.num_actions
@@ -106,7 +110,11 @@ class HumanoidEnvB200(_EnvBase):
 
     # ------------------------------------------------------------------ gym API
     def seed(self, seed: Optional[int] = None):
+        """BaseEnv.seed / gym reset(seed=): reseeds np_random AND the device-side task / Fall-init stream (Philox counter jump:
+        the key stays (cfg.seed, env id), the per-env counter restarts from a value derived from `seed`)."""
         self.np_random = np.random.default_rng(seed)
+        if seed is not None:
+            self._b.rng_counter.fill_(int((int(seed) * 2654435761) & 0x7FFFFFFF))
 
     def reset(self, seed=None, options=None):
         if seed is not None:
