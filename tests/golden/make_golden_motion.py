@@ -78,6 +78,38 @@ def main_smplh():
     print("motion_fk_smplh.npz:", {k: v.shape for k, v in g.items() if hasattr(v, "shape")})
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--sampling" not in sys.argv:
     main()
     main_smplh()
+
+
+def gen_sampling():
+    """PMCP weight rules of MotionLibBase (motion_lib_base.py:225-270) run unbound on a namespace -> motion_sampling.npz."""
+    import ast
+    import types
+    # importing the module needs joblib / smplx / torch-geometry stubs (make_golden.py replaces it by a mock), so -- as for
+    # _calc_frame_blend -- the methods under test are executed from the reference SOURCE TEXT
+    src = open(os.path.join(MG.REF, "smpl_sim/smpllib/motion_lib_base.py")).read()
+    want = ("update_hard_sampling_weight", "update_soft_sampling_weight", "update_sampling_prob", "set_termination_history")
+    fns = [n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name in want]
+    env = {"np": np, "print": lambda *a, **k: None}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "motion_lib_base.py", "exec"), env)
+    K = 6
+    ns = types.SimpleNamespace(_motion_data_keys=np.array([f"k{i}" for i in range(K)]), _num_unique_motions=K,
+                               _sampling_prob=np.ones(K) / K, _termination_history=np.zeros(K), curr_failed_keys=[])
+    for name in want:
+        setattr(ns, name, types.MethodType(env[name], ns))
+    out = {}
+    ns.update_hard_sampling_weight(["k1", "k4"]); out["hard"] = ns._sampling_prob.copy()
+    ns.update_hard_sampling_weight([]); out["hard_empty"] = ns._sampling_prob.copy()
+    ns.update_soft_sampling_weight(["k0", "k2"]); ns.update_soft_sampling_weight(["k2", "k5"])
+    out["soft2"] = ns._sampling_prob.copy(); out["soft2_hist"] = ns._termination_history.copy()
+    hist = np.array([1.0, 0.0, 3.0, 2.0, 0.0, 4.0])
+    ns.set_termination_history(dict(termination_history=hist.copy(), failed_keys=["k3"]))
+    out["restore"] = ns._sampling_prob.copy(); out["restore_hist"] = hist
+    np.savez_compressed(os.path.join(HERE, "motion_sampling.npz"), **out)
+    print("motion_sampling.npz", {k: v.round(3).tolist() for k, v in out.items()})
+
+
+if __name__ == "__main__" and "--sampling" in sys.argv:
+    gen_sampling()
