@@ -46,6 +46,8 @@ WORKLOADS = {
                       "(synthetic clip tables, SURVEY 8d) + MoCap reset of finished envs from the gathered frame, uhc_pd"),
     "cfg5": dict(env="getup", robot="smplx_humanoid", overrides={}, envs=4096, balg=5698,
                  desc="cfg5 shard: 4096 SMPL-X (52 bodies) envs/GPU, env=getup (Fall init), obs_v1, uhc_pd"),
+    "cfg2-selfcol": dict(env="speed", robot="smpl_humanoid", overrides={"env.self_collision": True}, envs=4096, balg=2682,
+                         desc="cfg2 with cfg.env.self_collision: geom-geom contacts (capsule / sphere pairs, MuJoCo's filters) simulated as two-body rows"),
 }
 _WL = "cfg2"
 
@@ -424,7 +426,7 @@ def main():
     extra = {}
     if not args.no_extra and _WL == "cfg2":
         # the configurations north_star states its target on (cfg4: 65 536 envs + motion feed on 8 GPUs; cfg5: SMPL-X), short runs
-        for wl in ("cfg4", "cfg5"):
+        for wl in ("cfg4", "cfg5", "cfg2-selfcol"):
             Kx = max(10, K // 8)
             x = measure(wl, args, torch, dist, world, rank, local, Kx, 3, False)
             extra[wl] = {"workload": WORKLOADS[wl]["desc"], "envs_per_gpu": x["N"], "global_envs": x["N"] * world, "steps": Kx,
