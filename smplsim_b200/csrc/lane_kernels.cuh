@@ -1487,6 +1487,26 @@ __device__ __noinline__ int l_solve(const float* ms, float* sm, const LLane& w, 
       const float* le = sm + C::lim + C::LIMW * e;
       if ((le[LLE_RS] < 0.f ? 1 : 0) != (((const int*)le)[LLE_FLAG] & 1)) L_STAT(12, 1);
     }
+    // [22..25]: first-pass misses whose every flipped row carries a force change |D rs| below 1e-3 / 1e-2 / 1e-1 / 1 N
+    if (any_rows && !same0) {
+      float worst = 0.f, fsum = 0.f;
+      for (int c = 0; c < ncon; c++) {
+        const float* ce = l_centry<C>(sm, w, c);
+        int info = ((const int*)ce)[LCE_INFO];
+        if (!(info & 1)) continue;
+        for (int k = 0; k < 4; k++) {
+          bool act = (info & (2 << k)) != 0, neg = ce[LCE_RS + k] < 0.f;
+          if (act != neg) worst = fmaxf(worst, fabsf(ce[LCE_D] * ce[LCE_RS + k]));
+          if (neg) fsum += fabsf(ce[LCE_D] * ce[LCE_RS + k]);
+        }
+      }
+      if (worst < 1e-3f) L_STAT(22, 1);
+      if (worst < 1e-2f) L_STAT(23, 1);
+      if (worst < 1e-1f) L_STAT(24, 1);
+      if (worst < 1.f) L_STAT(25, 1);
+      if (worst < 1e-4f * fsum) L_STAT(26, 1);
+      if (worst < 1e-3f * fsum) L_STAT(27, 1);
+    }
   }
 #endif
   // align bit 3: every warp of the CTA makes the same number of iterations (predicated), so all of them stay in the same sweep

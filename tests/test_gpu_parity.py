@@ -538,3 +538,38 @@ def test_env_step_with_self_collision_matches_oracle(backend):
             o, r, te, tr = e.step(act[i])
             assert np.abs(obs[i] - o).max() < 1e-2 * (t + 1), (t, i, np.abs(obs[i] - o).max())
             assert bool(term[i]) == te and bool(trunc[i]) == tr
+
+
+@pytest.mark.parametrize("knob", ["SMPLSIM_REC=smem", "SMPLSIM_ALIGN=0", "SMPLSIM_DIRTYPATH=0", "SMPLSIM_WPB=3"])
+def test_every_runtime_knob_keeps_parity(backend, knob, monkeypatch):
+    """The debug / A-B switches that stay selectable are read at smplsim_create: lane records in shared memory
+    instead of tensor memory, no CTA phase-alignment barriers, full instead of dirty-chain re-sweeps, a forced CTA size.  Each must
+    give the same physics: one substep from contact states + two env steps, against the oracle."""
+    k, v = knob.split("=")
+    monkeypatch.setenv(k, v)
+    cfg, om = make_models(control_mode="uhc_pd")
+    m = om.model
+    n = 24
+    q, v_, w = rollout_states(om, n, seed=11)
+    rng = np.random.default_rng(2)
+    ctrl = rng.uniform(-80, 80, (n, m.nu))
+    env = backend.batch(cfg, n)
+    env.set_state(backend.t(q), backend.t(v_)); env.qacc_warm.copy_(backend.t(w))
+    env.mj_step(backend.t(ctrl), 1)
+    gq, gv = env.qpos.cpu().numpy(), env.qvel.cpu().numpy()
+    for i in range(n):
+        e = _oracle_one_step(om, q[i], v_[i], w[i], ctrl[i])
+        assert relerr(gv[i], e.qvel) < 2e-4 and relerr(gq[i], e.qpos) < TOL, (knob, i, relerr(gv[i], e.qvel))
+    env2 = backend.batch(cfg, 8, seed=3)
+    env2.reset()
+    oes = [orc.OracleEnv(om, env_id=i) for i in range(8)]
+    om2 = orc.OracleModel.from_cfg(cfg, seed=env2.seed)
+    oes = [orc.OracleEnv(om2, env_id=i) for i in range(8)]
+    for e in oes:
+        e.reset()
+    for t in range(2):
+        act = np.clip(rng.normal(size=(8, m.nu)) * 0.1, -1, 1)
+        obs = env2.step(backend.t(act))[0].cpu().numpy()
+        for i, e in enumerate(oes):
+            o = e.step(act[i])[0]
+            assert np.abs(obs[i] - o).max() < 1e-3 * (t + 1), (knob, t, i)

@@ -31,3 +31,5 @@ print(f"env-substeps {s[0]}  with rows {s[1]} ({s[1] / max(1, s[0]):.2f})  first
 print("extra solves histogram 1..6+:", s[3:9], " mean over envs with rows:", sum((i + 1) * v for i, v in enumerate(s[3:9])) / max(1, s[1]))
 print(f"contacts {s[13]} (new {s[14]});  rows predicted active but free {s[9]}, predicted free but active {s[10]}, of both in new contacts {s[11]}; limit rows flipped {s[12]}")
 print(f"rows {s[16]}: inherit wrong {s[17]} ({s[17] / max(1, s[16]):.3f}), prediction wrong {s[18]} ({s[18] / max(1, s[16]):.3f}), both wrong {s[19]}; contacts with exact inherit {s[20]}, exact prediction {s[21]} of {s[13]}")
+miss = s[1] - s[2]
+print(f"first-pass misses {miss}: every flipped row below 1e-3 N: {s[22]}, 1e-2 N: {s[23]}, 0.1 N: {s[24]}, 1 N: {s[25]}; below 1e-4 / 1e-3 of the total contact force: {s[26]} / {s[27]}")
