@@ -53,9 +53,12 @@ struct LCfg {
                        lim = con + CONW * NCS, pfl = lim + LIMW * NLS, PFLW = r4((NS + 3) / 4), misc = pfl + PFLW, tsk = misc + 8,
                        rec = tsk + 12, total_ = rec + (RECT ? 0 : RECW * NB);
   static constexpr int total = total_ | 4;   // env stride: a multiple of 4 words (float4 rows) but not of 8 (bank spread)
-  // staging of the final kinematics / observation row: aliases the mailboxes, root factors and contact list (dead by then)
-  static constexpr int obs = mbi, xq = mbi + 4 * ((NB * 18 + 16 + 3) / 4);
-  static_assert(xq + 4 * NB <= lim, "observation / xquat staging does not fit the aliased region");
+  // staging of the final kinematics / observation row: aliases the mailboxes, root factors and contact list (dead by then).  When
+  // the observation row does not fit beside the xquat rows (SMPL-X) it is written straight to global memory instead.
+  static constexpr int OBSW = 4 * ((NB * 18 + 16 + 3) / 4);
+  static constexpr bool OBS_STAGED = OBSW + 4 * NB <= lim - mbi;
+  static constexpr int obs = mbi, xq = OBS_STAGED ? mbi + OBSW : mbi;
+  static_assert(xq + 4 * NB <= lim, "xquat staging does not fit the aliased region");
 };
 // misc words
 #define LMI_NCON 0
@@ -1868,8 +1871,8 @@ __device__ __forceinline__ Q4 l_heading_inv(const LHdr& H, Q4 root) {
 template <class C>
 __device__ __noinline__ void l_write_obs(const float* ms, float* sm, const LLane& w, float* obs_row) {
   const LHdr& H = l_hdr<C>(ms);
-  if (w.live) {
-    float* ob = sm + C::obs;
+  if (w.live && (C::OBS_STAGED || obs_row)) {
+    float* ob = C::OBS_STAGED ? sm + C::obs : obs_row;
     const float *qpos = sm + C::qpos, *xq = sm + C::xq, *qvel = sm + C::qvel, *sens = w.gsens;
     int nb = H.nb;
     Q4 r0; r0.w = xq[0]; r0.x = xq[1]; r0.y = xq[2]; r0.z = xq[3];
@@ -1904,7 +1907,7 @@ __device__ __noinline__ void l_write_obs(const float* ms, float* sm, const LLane
     }
   }
   __syncwarp();
-  if (obs_row) l_copy_out<C>(obs_row, sm + C::obs, H.obs_dim, w);
+  if (C::OBS_STAGED && obs_row) l_copy_out<C>(obs_row, sm + C::obs, H.obs_dim, w);
   __syncwarp();
 }
 

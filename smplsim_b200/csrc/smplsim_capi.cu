@@ -20,7 +20,7 @@
 // model classes the kernels are instantiated for: <bodies, dofs, geoms, contact slots, in-mailboxes, out-mailboxes, contact
 // entries in shared memory, limit rows, records in tensor memory, geom-geom rows compiled in>
 #define L_SMPL(RECT, SC) LCfg<24, 75, 24, 64, 5, 2, 20, 16, RECT, SC>
-#define L_SMPLX(RECT, SC) LCfg<52, 159, 52, 128, 16, 8, 24, 24, RECT, SC>
+#define L_SMPLX(RECT, SC) LCfg<52, 159, 52, 128, 13, 4, 14, 16, RECT, SC>   // sized so that 16 envs (4 warps) fit one SM
 
 struct SmplsimHandle {
   LaneImage img;
@@ -159,6 +159,9 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   if (e == cudaSuccess) e = cudaMemset(h->gpfl, 0, pw * num_envs * 4);
   if (e == cudaSuccess && cfg->self_collision) e = cudaMalloc(&h->gbody, (size_t)10 * H.nb * num_envs * 4);
   if (e != cudaSuccess) { if (h->dimg) cudaFree(h->dimg); if (h->gscr) cudaFree(h->gscr); if (h->gsens) cudaFree(h->gsens); if (h->gpfl) cudaFree(h->gpfl); if (h->gbody) cudaFree(h->gbody); delete h; return fail(SMPLSIM_ECUDA, std::string("smplsim_create: ") + cudaGetErrorString(e)); }
+  if (std::getenv("SMPLSIM_DEBUG"))
+    fprintf(stderr, "smplsim_create: class %d, %d bodies, schedule %d steps, mailboxes %d in / %d out, %d geom pairs, table %d B, %zu B per env, %d warps per CTA, %zu B shared memory per CTA, records in %s, self-collision %d\n",
+            h->cls, H.nb, H.T, H.nmbi, H.nmbo, H.npair, H.bytes, h->env_words * 4, h->wpb, h->smem, h->rect ? "tensor memory" : "shared memory", h->selfcol);
   *out = h;
   return SMPLSIM_OK;
 }
