@@ -573,3 +573,79 @@ def test_every_runtime_knob_keeps_parity(backend, knob, monkeypatch):
         for i, e in enumerate(oes):
             o = e.step(act[i])[0]
             assert np.abs(obs[i] - o).max() < 1e-3 * (t + 1), (knob, t, i)
+
+
+def _shape_variant(tmp_path, leg=1.18, arm=0.88, trunk=1.07, girth=1.15, density=1.2):
+    """A differently proportioned SMPL body (what SMPL_Robot writes for non-zero betas, smpl_local_robot.py:1280-1505: other bone
+    offsets, geom sizes and hence masses / inertias; same tree, joints and geom types), as a `*.model.json` for cfg.robot.xml_path."""
+    import json
+    from smplsim_b200 import model as M
+    p = M.load_parsed("smpl")
+    d = M._to_jsonable(p)
+    def fac(name):
+        if any(k in name for k in ("Hip", "Knee", "Ankle", "Toe")):
+            return leg
+        if any(k in name for k in ("Shoulder", "Elbow", "Wrist", "Hand", "Thorax")):
+            return arm
+        return trunk
+    for b in d["bodies"]:
+        f = fac(b["name"])
+        b["pos"] = [x * (leg if b["free"] else f) for x in b["pos"]]   # the root's pos is the standing height
+    names = [b["name"] for b in d["bodies"]]
+    for g in d["geoms"]:
+        f = fac(names[g["body"]] if isinstance(g["body"], int) else g["body"])
+        g["pos"] = [x * f for x in g["pos"]]
+        s = list(g["size"])
+        if g["type"] == 3:   # capsule: radius, half length
+            s[0] *= girth; s[1] *= f
+        else:
+            s = [x * girth for x in s]
+        g["size"] = s
+        g["density"] = g["density"] * density
+    path = tmp_path / "variant.model.json"
+    path.write_text(json.dumps(d))
+    return str(path)
+
+
+def test_custom_body_shape_matches_oracle(backend, tmp_path):
+    """SURVEY 8 f4 (body shapes): a handle takes any SMPL-family model (cfg.robot.xml_path: MJCF or model table), e.g. one batch per
+    body shape side by side.  A taller / heavier variant: one mj_step from contact-rich states at the SMPL tolerance, then env steps."""
+    path = _shape_variant(tmp_path)
+    cfg, om = make_models(control_mode="uhc_pd", **{"robot.xml_path": path})
+    base = make_models(control_mode="uhc_pd")[1].model
+    m = om.model
+    assert abs(m.body_mass.sum() / base.body_mass.sum() - 1) > 0.2 and not np.allclose(m.body_pos, base.body_pos)
+    n = 32
+    q, v, w = rollout_states(om, n, seed=5, every=9)   # sparse snapshots: the taller body first drops a few cm onto its feet
+    rng = np.random.default_rng(3)
+    ctrl = rng.uniform(-80, 80, (n, m.nu))
+    cfg_t, om_t = make_models(control_mode="torque", **{"robot.xml_path": path})
+    env = backend.batch(cfg_t, n)
+    env.set_state(backend.t(q), backend.t(v))
+    env.qacc_warm.copy_(backend.t(w))
+    env.mj_step(backend.t(ctrl), 1)
+    gq, gv = env.qpos.cpu().numpy(), env.qvel.cpu().numpy()
+    gmask = env.contact_mask.cpu().numpy().astype(np.uint64)
+    ncon = 0
+    for i in range(n):
+        e = _oracle_one_step(om_t, q[i], v[i], w[i], ctrl[i])
+        con = e.contacts()
+        if e.ncon and (np.abs(con["dist"] - m.margin) < 1e-5).any():
+            continue
+        assert int(gmask[i]) == e.contact_mask, (i, bin(int(gmask[i])), bin(e.contact_mask))
+        ncon += e.ncon > 0
+        assert relerr(gv[i], e.qvel) < TOL and relerr(gq[i], e.qpos) < TOL, (i, relerr(gv[i], e.qvel), relerr(gq[i], e.qpos))
+    assert ncon > n // 3
+    env2 = backend.batch(cfg, 8, seed=4)
+    obs0 = env2.reset().cpu().numpy().copy()
+    om4 = orc.OracleModel.from_cfg(cfg, seed=4)
+    oes = [orc.OracleEnv(om4, env_id=i) for i in range(8)]
+    for i, e in enumerate(oes):
+        assert np.abs(obs0[i] - e.reset()).max() < 1e-5
+    for t in range(2):
+        act = np.clip(rng.normal(size=(8, m.nu)) * 0.1, -1, 1)
+        obs, rew, term, trunc = [x.cpu().numpy() for x in env2.step(backend.t(act))]
+        for i, e in enumerate(oes):
+            o, r, te, tr = e.step(act[i])
+            assert np.abs(obs[i] - o).max() < 5e-4 * (t + 1), (t, i, np.abs(obs[i] - o).max())
+            assert abs(rew[i] - r) < 5e-4 * (t + 1) and bool(term[i]) == te and bool(trunc[i]) == tr
