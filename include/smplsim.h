@@ -165,6 +165,14 @@ int smplsim_version(void);   /* 110 = this header (100: before pid_* state and a
  * (base_env.py:139-142, humanoid_env.py:262-323). */
 int smplsim_create(const SmplsimModelDesc* model, const SmplsimEnvCfg* cfg, int num_envs, int cuda_device,
                    SmplsimHandle** out);
+/* Per-env body shapes: what one SMPL_Robot per env process gives the reference (humanoid_env.py:219-250: each HumanoidEnv builds
+ * its own MJCF from its betas / gender, smpllib/smpl_local_robot.py:1280-1505) in ONE batch.  Env e is simulated with
+ * models[env_model[e]].  All models must share tree, joints and geom layout (offsets, geom sizes, masses, inertias, gains and
+ * joint ranges may differ); envs of one shape are grouped into whole thread blocks internally, env indexing of every array is
+ * unchanged.  num_models == 1 (env_model may be NULL) is smplsim_create. */
+int smplsim_create_shapes(const SmplsimModelDesc* models, int num_models, const int32_t* env_model, const SmplsimEnvCfg* cfg,
+                          int num_envs, int cuda_device, SmplsimHandle** out);
+int smplsim_num_shapes(const SmplsimHandle* h);
 int smplsim_destroy(SmplsimHandle* h);
 int smplsim_obs_dim(const SmplsimHandle* h);
 int smplsim_num_envs(const SmplsimHandle* h);

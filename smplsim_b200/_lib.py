@@ -34,6 +34,8 @@ _SYMBOLS = {
     "smplsim_last_error": (C.c_char_p, []),
     "smplsim_version": (C.c_int, []),
     "smplsim_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "smplsim_create_shapes": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "smplsim_num_shapes": (C.c_int, [C.c_void_p]),
     "smplsim_destroy": (C.c_int, [C.c_void_p]),
     "smplsim_obs_dim": (C.c_int, [C.c_void_p]),
     "smplsim_num_envs": (C.c_int, [C.c_void_p]),

@@ -65,7 +65,10 @@ def env_cfg_from(cfg: Any, model: ModelDesc, seed: int = 0) -> SmplsimEnvCfgC:
     if r.humanoid_type not in ("smpl", "smplh", "smplx"):
         raise NotImplementedError(f"humanoid_type: {r.humanoid_type}")
     if _get(r, "has_shape_variation", False) or _get(r, "has_shape_obs", False) or _get(r, "has_weight_obs", False):
-        raise NotImplementedError("shape variation / shape obs need the SMPL model files (SURVEY.md 8 f4)")
+        # humanoid_env.py:304-305 only adds 10 to _num_self_obs for has_shape_variation -- compute_proprioception (:372-403) never fills
+        # them, so the reference's own MuJoCo path is inconsistent with the flag set; shape / limb-weight obs exist on the Isaac side only.
+        raise NotImplementedError("has_shape_variation / has_shape_obs / has_weight_obs change the observation only on the Isaac side of the "
+                                  "reference; per-env body shapes themselves: HumanoidBatchB200(models=[...], env_model=[...])")
     v = int(e.self_obs_v)
     if v not in (1, 2):
         raise NotImplementedError(f"self_obs_v: {v}")

@@ -7,7 +7,7 @@ PyTorch owns every tensor (device memory, streams); the C ABI receives raw point
 from __future__ import annotations
 
 import ctypes as C
-from typing import Any, Optional
+from typing import Sequence, Any, Optional
 
 import numpy as np
 import torch
@@ -30,12 +30,20 @@ class HumanoidBatchB200:
     """
 
     def __init__(self, cfg: Any, num_envs: Optional[int] = None, device: str = "cuda:0", seed: Optional[int] = None,
-                 model: Optional[ModelDesc] = None, rank: int = 0, with_aux: bool = True):
+                 model: Optional[ModelDesc] = None, rank: int = 0, with_aux: bool = True,
+                 models: Optional[Sequence[ModelDesc]] = None, env_model: Optional[Sequence[int]] = None):
+        """``models`` + ``env_model`` ([num_envs] indices into models): per-env body shapes in one batch -- what one SMPL_Robot per
+        env process gives the reference (humanoid_env.py:219-250).  Same tree / joints / geom layout in every model."""
         self._require_device(device)
         self.cfg = cfg
         e = cfg.env
         self.num_envs = int(num_envs if num_envs is not None else (e.get("num_envs", 1) if hasattr(e, "get") else 1))
         self.device = torch.device(device)
+        self.models = list(models) if models is not None else None
+        if self.models is not None:
+            if env_model is None or len(env_model) != self.num_envs:
+                raise ValueError("models= needs env_model with one entry per env")
+            model = self.models[0]
         self.model = model if model is not None else model_from_cfg(cfg)
         seed = int(cfg.get("seed", 0) if seed is None and hasattr(cfg, "get") else (seed or 0))
         self.seed = (seed + 0x9E3779B97F4A7C15 * rank) & 0xFFFFFFFFFFFFFFFF      # per-rank Philox key (env sharding)
@@ -44,7 +52,16 @@ class HumanoidBatchB200:
         self._h = C.c_void_p()
         L = self._L()
         dev_index = self._device_index()
-        self._check(L.smplsim_create(C.addressof(self._cmodel), C.addressof(self.envcfg), self.num_envs, dev_index, C.byref(self._h)))
+        if self.models is None:
+            self._check(L.smplsim_create(C.addressof(self._cmodel), C.addressof(self.envcfg), self.num_envs, dev_index, C.byref(self._h)))
+            self.env_model = None
+        else:
+            self._cmodels_each = [m.c_struct() for m in self.models]          # keeps the arrays the structs point at alive
+            arr = (type(self._cmodel) * len(self.models))(*self._cmodels_each)
+            em = np.ascontiguousarray(np.asarray(env_model, dtype=np.int32))
+            self._check(L.smplsim_create_shapes(C.addressof(arr), len(self.models), C.c_void_p(em.ctypes.data), C.addressof(self.envcfg),
+                                                self.num_envs, dev_index, C.byref(self._h)))
+            self.env_model = em
         self.num_obs = L.smplsim_obs_dim(self._h)
         self.num_actions = self.model.nu
         self.dt = float(self.model.timestep * self.envcfg.nsubsteps)

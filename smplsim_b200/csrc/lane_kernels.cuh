@@ -1765,6 +1765,9 @@ __device__ __noinline__ void l_substeps(const float* ms, float* sm, const LLane&
 // ====================================================================================================================
 // env-level kernels
 // ====================================================================================================================
+// per-env body shapes (smplsim_create_shapes): CTA b stages table blk_img[b]; slot i of the grid works on env slot_env[i] (< 0: none).
+// Both NULL: one table, slot == env.
+struct LMap { const int* slot_env; const int* blk_img; };
 struct LStepArgs {
   SmplsimState st;
   SmplsimAux aux;
@@ -1777,6 +1780,7 @@ struct LStepArgs {
   float* gsens;      // [n, 6 nb] or NULL
   float* gbody;      // [n, 10 nb] or NULL (self-collision)
   int* gpfl;         // [n, r4(NS / 4)] working set per contact slot
+  LMap map;
   int n, nsub, mode;
 };
 struct LResetArgs {
@@ -1790,9 +1794,10 @@ struct LResetArgs {
   float* gsens;
   float* gbody;
   int* gpfl;
+  LMap map;
   int n, init_mode;
 };
-struct LKinArgs { const float* qpos; float* xpos; float* xquat; int n; };
+struct LKinArgs { const float* qpos; float* xpos; float* xquat; LMap map; int n; };
 
 template <class C>
 __device__ __forceinline__ void l_copy(float* dst, const float* src, int n, const LLane& w) {
@@ -1976,8 +1981,9 @@ extern __shared__ float4 l_smem4[];
 
 // CTA prologue: stage the constant table, carve the env rows, claim tensor memory.  Shared memory: [table | 4 words | env rows]
 template <class C>
-__device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int img_bytes, LLane& w, const float*& ms, int n, float* gscr, float* gsens, int* gpfl, float* gbody = nullptr) {
+__device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int img_bytes, LLane& w, const float*& ms, int n, const LMap& map, float* gscr, float* gsens, int* gpfl, float* gbody = nullptr) {
   float* smem = L_SMEM;
+  if (map.blk_img) gimg += (size_t)map.blk_img[blockIdx.x] * (size_t)(img_bytes / 4);   // this CTA's body shape
   unsigned* slot = (unsigned*)(smem + img_bytes / 4);   // [0] tensor-memory base, [2..3] mbarrier of the table copy
 #ifndef SMPLSIM_EMU
   {
@@ -2030,7 +2036,8 @@ __device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int im
   w.lane = lane; w.li = lane % LM_LPE; w.gbase = sub * LM_LPE;
   w.gmask = ((1u << LM_LPE) - 1u) << (sub * LM_LPE);
   w.env = (blockIdx.x * wpb + wib) * C::EPW + sub;
-  w.live = w.env < n;
+  if (map.slot_env) w.env = map.slot_env[w.env];
+  w.live = w.env >= 0 && w.env < n;
   w.bar = true;
   // tensor memory: a warp reaches the 32 lanes of its quarter (warp id mod 4); warps 4.. take the upper 256 columns
   w.tm = tbase + ((unsigned)((wib & 3) * 32) << 16) + (unsigned)((wib >> 2) * 256);
@@ -2073,7 +2080,7 @@ __device__ __noinline__ void l_spd_prologue(const float* ms, float* sm, const LL
 template <class C>
 __global__ void __launch_bounds__(256, 1) k_step5(const float* __restrict__ gimg, int img_bytes, LStepArgs a) {
   const float* ms; LLane w;
-  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.gscr, a.gsens, a.gpfl, a.gbody);
+  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.map, a.gscr, a.gsens, a.gpfl, a.gbody);
   const LHdr& H = l_hdr<C>(ms);
   const size_t eo = w.live ? (size_t)w.env : 0;   // lanes without a live env keep running (predicated): warp collectives stay legal
   const bool spd = (H.cfg.control_mode == SMPLSIM_CTRL_UHC_PD);
@@ -2136,7 +2143,7 @@ __global__ void __launch_bounds__(256, 1) k_step5(const float* __restrict__ gimg
 template <class C>
 __global__ void __launch_bounds__(256, 1) k_reset5(const float* __restrict__ gimg, int img_bytes, LResetArgs a) {
   const float* ms; LLane w;
-  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.gscr, a.gsens, a.gpfl, a.gbody);
+  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.map, a.gscr, a.gsens, a.gpfl, a.gbody);
   const LHdr& H = l_hdr<C>(ms);
   if (w.live && a.mask && !a.mask[w.env]) w.live = false;
   size_t eo = w.live ? (size_t)w.env : 0;
@@ -2213,7 +2220,7 @@ __global__ void __launch_bounds__(256, 1) k_reset5(const float* __restrict__ gim
 template <class C>
 __global__ void __launch_bounds__(256, 1) k_kin5(const float* __restrict__ gimg, int img_bytes, LKinArgs a) {
   const float* ms; LLane w;
-  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, nullptr, nullptr, nullptr);
+  float* sm = l_setup<C>(gimg, img_bytes, w, ms, a.n, a.map, nullptr, nullptr, nullptr);
   const LHdr& H = l_hdr<C>(ms);
   size_t eo = w.live ? (size_t)w.env : 0;
   l_copy<C>(sm + C::qpos, a.qpos + eo * (H.nv + 1), H.nv + 1, w);

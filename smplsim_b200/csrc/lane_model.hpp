@@ -74,6 +74,7 @@ struct LaneImage {
   LHdr* hdr() { return (LHdr*)bytes.data(); }
   const LHdr* hdr() const { return (const LHdr*)bytes.data(); }
   LBody* bodies() { return (LBody*)(bytes.data() + hdr()->body_off); }
+  const LBody* bodies() const { return (const LBody*)(bytes.data() + hdr()->body_off); }
   LGeom* geoms() { return (LGeom*)(bytes.data() + hdr()->geom_off); }
 };
 

@@ -35,6 +35,12 @@ struct SmplsimHandle {
   int selfcol = 0;         // cfg.env.self_collision: kernels with the geom-geom rows compiled in
   int wpb = 0;             // warps per CTA
   size_t smem = 0, env_words = 0;
+  // per-env body shapes (smplsim_create_shapes): envs grouped by shape into whole CTAs
+  std::vector<int> env_model;   // [num_envs] or empty (one shape)
+  int nmodels = 1, nblocks = 0;
+  int* dslot_env = nullptr;     // [nblocks * warps per CTA * envs per warp] slot -> env (-1: none)
+  int* dblk_img = nullptr;      // [nblocks] CTA -> table
+  LMap map() const { LMap m; m.slot_env = dslot_env; m.blk_img = dblk_img; return m; }
 };
 
 static thread_local std::string g_err;
@@ -57,6 +63,16 @@ extern "C" int smplsim_version(void) { return 200; }   // 200: lane-chain kernel
 template <class C>
 static size_t cta_smem(const SmplsimHandle* h, int wpb) { return (size_t)h->img.hdr()->bytes + 16 + (size_t)wpb * C::EPW * C::total * 4; }
 
+// CTAs of a launch over all envs: every CTA holds envs of one body shape
+static long count_blocks(const SmplsimHandle* h, long per) {
+  if (h->env_model.empty()) return (h->num_envs + per - 1) / per;
+  std::vector<long> cnt(h->nmodels, 0);
+  for (int m : h->env_model) cnt[m]++;
+  long b = 0;
+  for (long c : cnt) b += (c + per - 1) / per;
+  return b;
+}
+
 // warps per CTA: fewest waves over the SMs first, then the fewest warps (an SM issues faster for few resident warps)
 template <class C>
 static int pick_wpb(SmplsimHandle* h) {
@@ -69,7 +85,7 @@ static int pick_wpb(SmplsimHandle* h) {
     if (forced && wpb != forced) continue;
     if (cta_smem<C>(h, wpb) > (size_t)h->max_smem) continue;
     if (C::RECT && C::RECW * H.T > (wpb > 4 ? 256 : 512)) continue;
-    long per = (long)wpb * C::EPW, blocks = (h->num_envs + per - 1) / per, waves = (blocks + h->nsm - 1) / h->nsm;
+    long per = (long)wpb * C::EPW, blocks = count_blocks(h, per), waves = (blocks + h->nsm - 1) / h->nsm;
     if (waves < best_waves) { best_waves = waves; best = wpb; }
   }
   if (!best) return -1;
@@ -85,17 +101,17 @@ static int pick_wpb(SmplsimHandle* h) {
 template <class C>
 static void run_step(SmplsimHandle* h, const LStepArgs& a, cudaStream_t st) {
   int wpb = h->wpb, per = wpb * C::EPW;
-  L_LAUNCH(k_step5<C>, (a.n + per - 1) / per, 32 * wpb, h->smem, st, h->dimg, h->img.hdr()->bytes, a);
+  L_LAUNCH(k_step5<C>, h->nblocks ? h->nblocks : (a.n + per - 1) / per, 32 * wpb, h->smem, st, h->dimg, h->img.hdr()->bytes, a);
 }
 template <class C>
 static void run_reset(SmplsimHandle* h, const LResetArgs& a, cudaStream_t st) {
   int wpb = h->wpb, per = wpb * C::EPW;
-  L_LAUNCH(k_reset5<C>, (a.n + per - 1) / per, 32 * wpb, h->smem, st, h->dimg, h->img.hdr()->bytes, a);
+  L_LAUNCH(k_reset5<C>, h->nblocks ? h->nblocks : (a.n + per - 1) / per, 32 * wpb, h->smem, st, h->dimg, h->img.hdr()->bytes, a);
 }
 template <class C>
 static void run_kin(SmplsimHandle* h, const LKinArgs& a, cudaStream_t st) {
   int wpb = h->wpb, per = wpb * C::EPW;
-  L_LAUNCH(k_kin5<C>, (a.n + per - 1) / per, 32 * wpb, h->smem, st, h->dimg, h->img.hdr()->bytes, a);
+  L_LAUNCH(k_kin5<C>, h->nblocks ? h->nblocks : (a.n + per - 1) / per, 32 * wpb, h->smem, st, h->dimg, h->img.hdr()->bytes, a);
 }
 // dispatch over (model class, record placement, self-collision)
 #define L_DISPATCH(h, CALL)                                                   \
@@ -112,8 +128,28 @@ static void run_kin(SmplsimHandle* h, const LKinArgs& a, cudaStream_t st) {
     }                                                                         \
   } while (0)
 
-extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cfg, int num_envs, int cuda_device, SmplsimHandle** out) {
-  if (!s || !cfg || !out || num_envs <= 0) return fail(SMPLSIM_EINVAL, "smplsim_create: null argument or num_envs <= 0");
+static void free_handle(SmplsimHandle* h) {
+  cudaFree(h->dimg); cudaFree(h->gscr); cudaFree(h->gsens); cudaFree(h->gpfl); cudaFree(h->gbody); cudaFree(h->dslot_env); cudaFree(h->dblk_img);
+  delete h;
+}
+
+// tables of two body shapes can share the kernels' schedule iff the tree, the joints and the geom layout agree
+static bool same_structure(const LaneImage& a, const LaneImage& b) {
+  const LHdr& A = *a.hdr(); const LHdr& B = *b.hdr();
+  if (A.bytes != B.bytes || A.nb != B.nb || A.nv != B.nv || A.nu != B.nu || A.ng != B.ng || A.nslot != B.nslot || A.nmbi != B.nmbi || A.nmbo != B.nmbo ||
+      A.T != B.T || A.npair != B.npair || A.obs_dim != B.obs_dim || std::memcmp(A.sched, B.sched, sizeof A.sched) != 0) return false;
+  for (int i = 0; i < A.nb; i++) {
+    const LBody& x = a.bodies()[i]; const LBody& y = b.bodies()[i];
+    if (x.parent != y.parent || x.dofadr != y.dofadr || x.flags != y.flags || x.geom0 != y.geom0 || x.ngeom != y.ngeom || x.limited != y.limited ||
+        x.in_mbox != y.in_mbox || x.out_mbox != y.out_mbox || x.pmbox != y.pmbox || x.nmb != y.nmb || x.step != y.step || x.lane != y.lane) return false;
+  }
+  return true;
+}
+
+static int create_impl(const SmplsimModelDesc* s, int nmodels, const int32_t* env_model, const SmplsimEnvCfg* cfg, int num_envs, int cuda_device, SmplsimHandle** out) {
+  if (!s || !cfg || !out || num_envs <= 0 || nmodels < 1) return fail(SMPLSIM_EINVAL, "smplsim_create: null argument or num_envs <= 0");
+  if (nmodels > 1 && !env_model) return fail(SMPLSIM_EINVAL, "smplsim_create_shapes: env_model is NULL");
+  if (env_model) for (int i = 0; i < num_envs; i++) if (env_model[i] < 0 || env_model[i] >= nmodels) return fail(SMPLSIM_EINVAL, "smplsim_create_shapes: env_model entry out of range");
   if (cfg->self_obs_v != 1 && cfg->self_obs_v != 2) return fail(SMPLSIM_EINVAL, "self_obs_v must be 1 or 2");
   if (cfg->control_mode < 0 || cfg->control_mode > 3) return fail(SMPLSIM_EINVAL, "control_mode must be uhc_pd|pd|torque|simple_pid");
   if (cfg->task < 0 || cfg->task > 3) return fail(SMPLSIM_EINVAL, "unknown task");
@@ -126,6 +162,16 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   { const char* dp = std::getenv("SMPLSIM_DIRTYPATH"); if (dp) H.dirtypath = std::atoi(dp); }
   { const char* al = std::getenv("SMPLSIM_ALIGN"); if (al) H.align = std::atoi(al); }   // CTA phase-alignment barriers (bit 0 substep, 1 solve, 2 stable-PD sweep)
   for (int b = 0; b < H.nb; b++) if (h->img.bodies()[b].ngeom > 1) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "more than one geom on a body"); }
+  std::vector<LaneImage> more(nmodels > 1 ? nmodels - 1 : 0);   // tables of the other body shapes
+  for (int k = 1; k < nmodels; k++) {
+    std::string w2 = lane_build(s + k, cfg, more[k - 1]);
+    if (!w2.empty()) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "body shape " + std::to_string(k) + ": " + w2); }
+    LHdr& Hk = *more[k - 1].hdr();
+    Hk.dirtypath = H.dirtypath; Hk.align = H.align;
+    if (!same_structure(h->img, more[k - 1])) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "body shape " + std::to_string(k) + " differs from shape 0 in tree / joints / geom layout (only offsets, sizes, masses and gains may differ)"); }
+  }
+  h->nmodels = nmodels;
+  if (env_model && nmodels > 1) h->env_model.assign(env_model, env_model + num_envs);
   typedef L_SMPL(0, 0) CS; typedef L_SMPLX(0, 0) CX;
   if (H.nb == CS::NB && H.nv == CS::NV && H.ng <= CS::NG && H.nslot <= CS::NS && H.nmbi <= CS::NMBI && H.nmbo <= CS::NMBO) h->cls = 1;
   else if (H.nb == CX::NB && H.nv == CX::NV && H.ng <= CX::NG && H.nslot <= CX::NS && H.nmbi <= CX::NMBI && H.nmbo <= CX::NMBO) h->cls = 2;
@@ -149,8 +195,29 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   if (ok <= 0) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "per-env rows exceed shared memory / tensor memory"); }
   size_t gs = 0;
   L_DISPATCH(h, gs = (size_t)C_::CONW * (C_::NS - C_::NCS));
-  e = cudaMalloc(&h->dimg, H.bytes);
+  e = cudaMalloc(&h->dimg, (size_t)H.bytes * nmodels);
   if (e == cudaSuccess) e = cudaMemcpy(h->dimg, h->img.bytes.data(), H.bytes, cudaMemcpyHostToDevice);
+  for (int k = 1; k < nmodels && e == cudaSuccess; k++) e = cudaMemcpy((char*)h->dimg + (size_t)H.bytes * k, more[k - 1].bytes.data(), H.bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !h->env_model.empty()) {   // envs grouped by shape into whole CTAs (empty slots: -1)
+    int per = 1;
+    L_DISPATCH(h, per = h->wpb * C_::EPW);
+    std::vector<int> slot_env, blk_img;
+    for (int k = 0; k < nmodels; k++) {
+      int fill = 0;
+      for (int i = 0; i < num_envs; i++) {
+        if (h->env_model[i] != k) continue;
+        if (fill == 0) blk_img.push_back(k);
+        slot_env.push_back(i);
+        fill = (fill + 1) % per;
+      }
+      while (fill != 0) { slot_env.push_back(-1); fill = (fill + 1) % per; }
+    }
+    h->nblocks = (int)blk_img.size();
+    e = cudaMalloc(&h->dslot_env, slot_env.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(h->dslot_env, slot_env.data(), slot_env.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&h->dblk_img, blk_img.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(h->dblk_img, blk_img.data(), blk_img.size() * sizeof(int), cudaMemcpyHostToDevice);
+  }
   if (e == cudaSuccess) e = cudaMalloc(&h->gscr, gs * (size_t)num_envs * 4 + 16);
   if (e == cudaSuccess) e = cudaMalloc(&h->gsens, (size_t)6 * H.nb * num_envs * 4);
   size_t pw = 0;
@@ -158,7 +225,7 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   if (e == cudaSuccess) e = cudaMalloc(&h->gpfl, pw * num_envs * 4);
   if (e == cudaSuccess) e = cudaMemset(h->gpfl, 0, pw * num_envs * 4);
   if (e == cudaSuccess && cfg->self_collision) e = cudaMalloc(&h->gbody, (size_t)10 * H.nb * num_envs * 4);
-  if (e != cudaSuccess) { if (h->dimg) cudaFree(h->dimg); if (h->gscr) cudaFree(h->gscr); if (h->gsens) cudaFree(h->gsens); if (h->gpfl) cudaFree(h->gpfl); if (h->gbody) cudaFree(h->gbody); delete h; return fail(SMPLSIM_ECUDA, std::string("smplsim_create: ") + cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { free_handle(h); return fail(SMPLSIM_ECUDA, std::string("smplsim_create: ") + cudaGetErrorString(e)); }
   if (std::getenv("SMPLSIM_DEBUG"))
     fprintf(stderr, "smplsim_create: class %d, %d bodies, schedule %d steps, mailboxes %d in / %d out, %d geom pairs, table %d B, %zu B per env, %d warps per CTA, %zu B shared memory per CTA, records in %s, self-collision %d\n",
             h->cls, H.nb, H.T, H.nmbi, H.nmbo, H.npair, H.bytes, h->env_words * 4, h->wpb, h->smem, h->rect ? "tensor memory" : "shared memory", h->selfcol);
@@ -166,15 +233,19 @@ extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cf
   return SMPLSIM_OK;
 }
 
+extern "C" int smplsim_create(const SmplsimModelDesc* s, const SmplsimEnvCfg* cfg, int num_envs, int cuda_device, SmplsimHandle** out) {
+  return create_impl(s, 1, nullptr, cfg, num_envs, cuda_device, out);
+}
+extern "C" int smplsim_create_shapes(const SmplsimModelDesc* models, int num_models, const int32_t* env_model, const SmplsimEnvCfg* cfg, int num_envs,
+                                     int cuda_device, SmplsimHandle** out) {
+  return create_impl(models, num_models, env_model, cfg, num_envs, cuda_device, out);
+}
+extern "C" int smplsim_num_shapes(const SmplsimHandle* h) { return h ? h->nmodels : SMPLSIM_EINVAL; }
+
 extern "C" int smplsim_destroy(SmplsimHandle* h) {
   if (!h) return SMPLSIM_OK;
   DeviceGuard guard(h->device);
-  cudaFree(h->dimg);
-  cudaFree(h->gscr);
-  cudaFree(h->gsens);
-  cudaFree(h->gpfl);
-  cudaFree(h->gbody);
-  delete h;
+  free_handle(h);
   return SMPLSIM_OK;
 }
 extern "C" int smplsim_obs_dim(const SmplsimHandle* h) { return h ? h->img.hdr()->obs_dim : SMPLSIM_EINVAL; }
@@ -204,7 +275,7 @@ extern "C" int smplsim_step(SmplsimHandle* h, const SmplsimState* st, const floa
   LStepArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
   a.action = action_dev; a.obs = obs_dev; a.reward = reward_dev; a.terminated = terminated_dev; a.truncated = truncated_dev;
-  a.gscr = h->gscr; a.gpfl = h->gpfl; a.gbody = h->gbody; a.n = h->num_envs; a.nsub = h->img.hdr()->cfg.nsubsteps; a.mode = 0;
+  a.gscr = h->gscr; a.gpfl = h->gpfl; a.gbody = h->gbody; a.n = h->num_envs; a.nsub = h->img.hdr()->cfg.nsubsteps; a.mode = 0; a.map = h->map();
   a.gsens = want_sens(h, aux) ? h->gsens : nullptr;
   L_DISPATCH(h, run_step<C_>(h, a, (cudaStream_t)stream));
   CUDA_TRY(cudaGetLastError());
@@ -216,7 +287,7 @@ extern "C" int smplsim_mj_step(SmplsimHandle* h, const SmplsimState* st, const f
   DeviceGuard guard(h->device);
   LStepArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
-  a.action = ctrl_dev; a.gscr = h->gscr; a.gpfl = h->gpfl; a.gbody = h->gbody; a.n = h->num_envs; a.nsub = nsub; a.mode = 1;
+  a.action = ctrl_dev; a.gscr = h->gscr; a.gpfl = h->gpfl; a.gbody = h->gbody; a.n = h->num_envs; a.nsub = nsub; a.mode = 1; a.map = h->map();
   a.gsens = want_sens(h, aux) ? h->gsens : nullptr;
   L_DISPATCH(h, run_step<C_>(h, a, (cudaStream_t)stream));
   CUDA_TRY(cudaGetLastError());
@@ -234,7 +305,7 @@ extern "C" int smplsim_reset(SmplsimHandle* h, const SmplsimState* st, const uin
   DeviceGuard guard(h->device);
   LResetArgs a; std::memset(&a, 0, sizeof a);
   a.st = *st; if (aux) a.aux = *aux;
-  a.mask = mask_dev; a.qpos0 = qpos0_dev; a.qvel0 = qvel0_dev; a.obs = obs_dev; a.gscr = h->gscr; a.gpfl = h->gpfl; a.gbody = h->gbody; a.n = h->num_envs; a.init_mode = mode;
+  a.mask = mask_dev; a.qpos0 = qpos0_dev; a.qvel0 = qvel0_dev; a.obs = obs_dev; a.gscr = h->gscr; a.gpfl = h->gpfl; a.gbody = h->gbody; a.n = h->num_envs; a.init_mode = mode; a.map = h->map();
   a.gsens = want_sens(h, aux) ? h->gsens : nullptr;
   L_DISPATCH(h, run_reset<C_>(h, a, (cudaStream_t)stream));
   CUDA_TRY(cudaGetLastError());
@@ -245,7 +316,8 @@ extern "C" int smplsim_kinematics(SmplsimHandle* h, const float* qpos_dev, float
   if (!h || !qpos_dev || !xpos_dev || !xquat_dev || n < 0) return fail(SMPLSIM_EINVAL, "smplsim_kinematics: bad argument");
   if (n == 0) return SMPLSIM_OK;
   DeviceGuard guard(h->device);
-  LKinArgs a; a.qpos = qpos_dev; a.xpos = xpos_dev; a.xquat = xquat_dev; a.n = n;
+  if (h->nblocks && n != h->num_envs) return fail(SMPLSIM_EINVAL, "smplsim_kinematics: with per-env body shapes n must be the handle's num_envs (row i uses env i's shape)");
+  LKinArgs a; a.qpos = qpos_dev; a.xpos = xpos_dev; a.xquat = xquat_dev; a.n = n; a.map = h->map();
   L_DISPATCH(h, run_kin<C_>(h, a, (cudaStream_t)stream));
   CUDA_TRY(cudaGetLastError());
   return SMPLSIM_OK;
