@@ -48,6 +48,8 @@ WORKLOADS = {
                  desc="cfg5 shard: 4096 SMPL-X (52 bodies) envs/GPU, env=getup (Fall init), obs_v1, uhc_pd"),
     "cfg2-selfcol": dict(env="speed", robot="smpl_humanoid", overrides={"env.self_collision": True}, envs=4096, balg=2682,
                          desc="cfg2 with cfg.env.self_collision: geom-geom contacts (capsule / sphere pairs, MuJoCo's filters) simulated as two-body rows"),
+    "cfg2-shapes": dict(env="speed", robot="smpl_humanoid", overrides={}, envs=4096, balg=2682, shapes=4,
+                        desc="cfg2 with per-env body shapes: 4 body shapes x 1024 envs interleaved in one batch (smplsim_create_shapes)"),
 }
 _WL = "cfg2"
 
@@ -233,7 +235,20 @@ def measure(wl, args, torch, dist, world, rank, local, K, W, headline):
     spec = WORKLOADS[wl]
     N = args.envs_per_gpu if headline else spec["envs"]
     cfg = make_cfg(wl)
-    env = HumanoidBatchB200(cfg, num_envs=N, device=str(dev), seed=0, rank=rank, with_aux=False)
+    kw = {}
+    if spec.get("shapes"):   # synthetic body shapes (no SMPL files here), interleaved over the envs
+        from smplsim_b200.abi import model_from_cfg
+        from smplsim_b200 import model as M
+        base, m0 = M.load_parsed("smpl"), model_from_cfg(cfg)
+        S = int(spec["shapes"])
+        var = [dict(), dict(leg=1.15, arm=0.9, trunk=1.05, girth=1.1, density=1.1), dict(leg=0.88, arm=1.08, trunk=0.95, girth=0.92, density=0.95),
+               dict(leg=1.05, arm=1.05, trunk=1.1, girth=1.2, density=1.0)]
+        e = cfg.env
+        kw["models"] = [M.build_model(M.shape_variant(base, **var[k % len(var)]), timestep=m0.timestep, contact_bodies=list(e.contact_bodies),
+                                      control_mode=e.control_mode, clip_actions=bool(e.clip_actions), power_scale=float(e.power_scale))
+                        for k in range(S)]
+        kw["env_model"] = (np.arange(N) % S).astype(np.int32)
+    env = HumanoidBatchB200(cfg, num_envs=N, device=str(dev), seed=0, rank=rank, with_aux=False, **kw)
     nu = env.num_actions
     gen = torch.Generator(device=dev)
     gen.manual_seed(0 + rank)
@@ -426,7 +441,7 @@ def main():
     extra = {}
     if not args.no_extra and _WL == "cfg2":
         # the configurations north_star states its target on (cfg4: 65 536 envs + motion feed on 8 GPUs; cfg5: SMPL-X), short runs
-        for wl in ("cfg4", "cfg5", "cfg2-selfcol"):
+        for wl in ("cfg4", "cfg5", "cfg2-selfcol", "cfg2-shapes"):
             Kx = max(10, K // 8)
             x = measure(wl, args, torch, dist, world, rank, local, Kx, 3, False)
             extra[wl] = {"workload": WORKLOADS[wl]["desc"], "envs_per_gpu": x["N"], "global_envs": x["N"] * world, "steps": Kx,

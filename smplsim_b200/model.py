@@ -475,5 +475,36 @@ def load_parsed(name_or_path: str) -> ParsedMJCF:
         return _from_jsonable(json.load(f))
 
 
+def shape_variant(p: ParsedMJCF, leg: float = 1.0, arm: float = 1.0, trunk: float = 1.0, girth: float = 1.0,
+                  density: float = 1.0) -> ParsedMJCF:
+    """A differently proportioned body of the same tree: bone offsets of the leg / arm / trunk bodies scaled, geoms moved and
+    stretched with their bones, radii / box extents scaled by ``girth``, densities by ``density`` (masses and inertias follow from
+    the geoms, as in MuJoCo's compiler).  A stand-in for what SMPL_Robot writes for other betas (smpllib/smpl_local_robot.py:
+    1280-1505) where the SMPL model files are not available; feed the results to HumanoidBatchB200(models=, env_model=)."""
+    import copy
+    q = copy.deepcopy(p)
+
+    def fac(name):
+        if any(k in name for k in ("Hip", "Knee", "Ankle", "Toe")):
+            return leg
+        if any(k in name for k in ("Shoulder", "Elbow", "Wrist", "Hand", "Thorax", "Index", "Middle", "Pinky", "Ring", "Thumb")):
+            return arm
+        return trunk
+
+    for b in q.bodies:
+        b.pos = np.asarray(b.pos, dtype=np.float64) * (leg if b.free else fac(b.name))   # the root's pos is the standing height
+    for g in q.geoms:
+        f = fac(q.bodies[g.body].name)
+        g.pos = np.asarray(g.pos, dtype=np.float64) * f
+        sz = np.asarray(g.size, dtype=np.float64).copy()
+        if g.type == GEOM_CAPSULE:
+            sz[0] *= girth; sz[1] *= f
+        else:
+            sz *= girth
+        g.size = sz
+        g.density = float(g.density) * density
+    return q
+
+
 def load_model(name_or_path: str = "smpl", **kw) -> ModelDesc:
     return build_model(load_parsed(name_or_path), **kw)
