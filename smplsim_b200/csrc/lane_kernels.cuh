@@ -86,6 +86,7 @@ struct LCfg {
 #define LBR_X 9
 #define LBR_R10 12
 #define LBR_CI 22
+#define LBR_C2 23   // c of the third hinge (tensor-memory records: K, c0, c1 in columns 0..19, pb in 20..25; no column group is shared)
 // contact entry: [info | cpos 3 | t1 3 | D | aref 4 | phi 4 | r 4 | rs 4]; info: bit0 present, bits1-4 working set, bits 8-15 geom, 16-23 slot
 #define LCE_INFO 0
 #define LCE_CP 1
@@ -218,14 +219,14 @@ static inline float __uint_as_float(unsigned u) { return emu_float(u); }
 template <class C>
 __device__ __forceinline__ void l_rec_ld_Kc(const LLane& w, float* sm, int t, int b, float* K, float* c) {
   if (C::RECT) {
-    unsigned r[24], a = w.tm + (unsigned)(C::RECW * t);
+    unsigned r[20], a = w.tm + (unsigned)(C::RECW * t);
     L_TM_LD16(a, r);
-    L_TM_LD8(a + 16u, r + 16);
+    L_TM_LD4(a + 16u, r + 16);
+    c[2] = (b >= 0) ? sm[C::body + C::BODYW * b + LBR_C2] : 0.f;
     L_TM_WAIT_LD();
 #pragma unroll
     for (int i = 0; i < 18; i++) K[i] = __uint_as_float(r[i]);
-#pragma unroll
-    for (int i = 0; i < 3; i++) c[i] = __uint_as_float(r[18 + i]);
+    c[0] = __uint_as_float(r[18]); c[1] = __uint_as_float(r[19]);
   } else {
     const float4* p = (const float4*)(sm + C::rec + C::RECW * (b < 0 ? 0 : b));
     float4 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4], v5 = p[5];
@@ -234,27 +235,24 @@ __device__ __forceinline__ void l_rec_ld_Kc(const LLane& w, float* sm, int t, in
     K[16] = v4.x; K[17] = v4.y; c[0] = v4.z; c[1] = v4.w; c[2] = v5.x;
   }
 }
+// Stores are not waited for here: the sweeps end with one tcgen05.wait::st (a record is read again in a later sweep only).
 template <class C>
 __device__ __forceinline__ void l_rec_st_Kc(const LLane& w, float* sm, int t, int b, const float* K, const float* c, bool wr, bool preload) {
   if (C::RECT) {
-    unsigned r[24], a = w.tm + (unsigned)(C::RECW * t);
+    unsigned r[20], a = w.tm + (unsigned)(C::RECW * t);
     if (preload) {   // some lanes keep their record (clean chains of a re-sweep): read - select - write
       L_TM_LD16(a, r);
-      L_TM_LD8(a + 16u, r + 16);
-      L_TM_WAIT_LD();
-    } else {         // pb (cols 22, 23 of the x8 piece) is always preserved
-      L_TM_LD4(a + 20u, r + 20);
+      L_TM_LD4(a + 16u, r + 16);
       L_TM_WAIT_LD();
     }
     if (wr) {
 #pragma unroll
       for (int i = 0; i < 18; i++) r[i] = __float_as_uint(K[i]);
-#pragma unroll
-      for (int i = 0; i < 3; i++) r[18 + i] = __float_as_uint(c[i]);
+      r[18] = __float_as_uint(c[0]); r[19] = __float_as_uint(c[1]);
+      if (b >= 0) sm[C::body + C::BODYW * b + LBR_C2] = c[2];
     }
     L_TM_ST16(a, r);
-    L_TM_ST8(a + 16u, r + 16);
-    L_TM_WAIT_ST();
+    L_TM_ST4(a + 16u, r + 16);
   } else if (wr && b >= 0) {
     float4* p = (float4*)(sm + C::rec + C::RECW * b);
     p[0] = make_float4(K[0], K[1], K[2], K[3]); p[1] = make_float4(K[4], K[5], K[6], K[7]);
@@ -265,32 +263,33 @@ __device__ __forceinline__ void l_rec_st_Kc(const LLane& w, float* sm, int t, in
 }
 template <class C>
 __device__ __forceinline__ S6 l_rec_ld_pb(const LLane& w, float* sm, int t, int b) {
-  float q[8];
+  float q[6];
   if (C::RECT) {
     unsigned r[8], a = w.tm + (unsigned)(C::RECW * t + 20);
     L_TM_LD8(a, r);
     L_TM_WAIT_LD();
 #pragma unroll
-    for (int i = 0; i < 8; i++) q[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 6; i++) q[i] = __uint_as_float(r[i]);
   } else {
-    const float* p = sm + C::rec + C::RECW * (b < 0 ? 0 : b) + 20;
+    const float* p = sm + C::rec + C::RECW * (b < 0 ? 0 : b) + 22;
 #pragma unroll
-    for (int i = 0; i < 8; i++) q[i] = p[i];
+    for (int i = 0; i < 6; i++) q[i] = p[i];
   }
-  return s6(v3(q[2], q[3], q[4]), v3(q[5], q[6], q[7]));
+  return s6(v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]));
 }
 template <class C>
 __device__ __forceinline__ void l_rec_st_pb(const LLane& w, float* sm, int t, int b, S6 pb, bool wr) {
   if (C::RECT) {
     unsigned r[8], a = w.tm + (unsigned)(C::RECW * t + 20);
-    L_TM_LD8(a, r);   // cols 20, 21 (c[2], spare) and a non-writing lane's pb are preserved
-    L_TM_WAIT_LD();
+    if (!w.bar) {   // partial re-forward (mj_checkAcc path): the other envs of the warp keep their pb
+      L_TM_LD8(a, r);
+      L_TM_WAIT_LD();
+    }
     if (wr) {
-      r[2] = __float_as_uint(pb.a.x); r[3] = __float_as_uint(pb.a.y); r[4] = __float_as_uint(pb.a.z);
-      r[5] = __float_as_uint(pb.l.x); r[6] = __float_as_uint(pb.l.y); r[7] = __float_as_uint(pb.l.z);
+      r[0] = __float_as_uint(pb.a.x); r[1] = __float_as_uint(pb.a.y); r[2] = __float_as_uint(pb.a.z);
+      r[3] = __float_as_uint(pb.l.x); r[4] = __float_as_uint(pb.l.y); r[5] = __float_as_uint(pb.l.z);
     }
     L_TM_ST8(a, r);
-    L_TM_WAIT_ST();
   } else if (wr && b >= 0) {
     float* p = sm + C::rec + C::RECW * b + 22;
     st3(p, pb.a); st3(p + 3, pb.l);
@@ -771,6 +770,7 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
     if (flags & LF_VEL) l_rec_st_pb<C>(w, sm, t, b, pbv, actv);
     __syncwarp();
   }
+  if (C::RECT && (flags & LF_VEL)) L_TM_WAIT_ST();   // pb is read by the inward sweep that follows
   LFkOut o;
   if (flags & LF_COLLIDE) {
     if (w.live && w.li == 0) { ((int*)sm)[C::misc + LMI_NCON] = ncon; ((int*)sm)[C::misc + LMI_NLIM] = min(nlim, C::NLS); ((int*)sm)[C::misc + LMI_NSELF] = 0; }
@@ -1176,6 +1176,7 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
     if (!resweep || __any_sync(L_FULL, need0)) d0 = l_root_in<C>(ms, sm, w, need0, flags);
     if (!spd && !resweep && d0 && w.li == 0) st.dirty_bits |= 1u;
   }
+  if (C::RECT) L_TM_WAIT_ST();   // the records of this sweep are read by the next one
   st_ = st;
 }
 
