@@ -96,6 +96,8 @@ struct LCfg {
 #define LCE_PHI 12
 #define LCE_R 16
 #define LCE_RS 20
+// root scratch (ROOTW words): [A 21 | p 6 | - ] the 6 x 6 system of the free joint, [36..41] its solution (spatial acceleration)
+#define LRT_A 36
 // limit entry: [dof | sg | D | aref | phi | flag | r | rs]
 #define LLE_DOF 0
 #define LLE_SG 1
@@ -483,18 +485,20 @@ __device__ __forceinline__ S6 l_body_post(const LBody& lb, float* sm, const LLan
 }
 
 // broad phase of the body's geom against the floor: number of contact entries to reserve (exact: > 0 iff at least one contact)
-struct LGeomCtx { float R[9]; V3 c, ax; float d0, na; };
+struct LGeomCtx { float R[9]; V3 c, ax; float d0, na; V3 e0, e1, e2; float l0, l1, l2; };   // box: half edges in world axes, their heights along the plane normal
 __device__ __forceinline__ int l_broad(const LHdr& H, const LGeom& G, const LPose& P, float h0, LGeomCtx& X) {
   const V3 pn = ld3(H.plane_n);
   q2mat(P.q, X.R);
   X.c = P.x + mrot(X.R, ld3(G.pos));
   X.d0 = h0 + dot(pn, X.c);
   X.ax = v3(0.f, 0.f, 0.f); X.na = 0.f;
+  X.e0 = X.e1 = X.e2 = v3(0.f, 0.f, 0.f); X.l0 = X.l1 = X.l2 = 0.f;
   if (G.type == SMPLSIM_GEOM_BOX) {
-    float ext = 0.f;
-#pragma unroll
-    for (int j = 0; j < 3; j++) ext += fabsf(dot(pn, mrot(X.R, v3(G.mat[j], G.mat[3 + j], G.mat[6 + j])))) * G.size[j];
-    return (X.d0 - ext <= H.margin) ? 4 : 0;
+    X.e0 = G.size[0] * mrot(X.R, v3(G.mat[0], G.mat[3], G.mat[6]));
+    X.e1 = G.size[1] * mrot(X.R, v3(G.mat[1], G.mat[4], G.mat[7]));
+    X.e2 = G.size[2] * mrot(X.R, v3(G.mat[2], G.mat[5], G.mat[8]));
+    X.l0 = dot(pn, X.e0); X.l1 = dot(pn, X.e1); X.l2 = dot(pn, X.e2);
+    return (X.d0 - (fabsf(X.l0) + fabsf(X.l1) + fabsf(X.l2)) <= H.margin) ? 4 : 0;
   }
   X.ax = mrot(X.R, v3(G.mat[2], G.mat[5], G.mat[8]));
   X.na = dot(pn, X.ax);
@@ -520,12 +524,11 @@ __device__ __forceinline__ int l_narrow(const LHdr& H, const LGeom& G, int g, co
   for (int i = 0; i < npt && cnt < alloc; i++) {
     V3 cp; float dist;
     if (G.type == SMPLSIM_GEOM_BOX) {
-      V3 vl = v3((i & 1) ? G.size[0] : -G.size[0], (i & 2) ? G.size[1] : -G.size[1], (i & 4) ? G.size[2] : -G.size[2]);
-      V3 wv = mrot(X.R, mrot(G.mat, vl));
-      float l = dot(pn, wv);
+      const float s0 = (i & 1) ? 1.f : -1.f, s1 = (i & 2) ? 1.f : -1.f, s2 = (i & 4) ? 1.f : -1.f;   // corner = centre +- e0 +- e1 +- e2
+      const float l = s0 * X.l0 + s1 * X.l1 + s2 * X.l2;
       if (X.d0 + l > H.margin || l > 0.f) continue;
       dist = X.d0 + l;
-      cp = X.c + wv - (0.5f * dist) * pn;
+      cp = X.c + (s0 * X.e0 + s1 * X.e1 + s2 * X.e2) - (0.5f * dist) * pn;
     } else {
       float hl = (G.type == SMPLSIM_GEOM_CAPSULE) ? G.size[1] : 0.f, sg = i ? -hl : hl;
       dist = X.d0 + sg * X.na - G.size[0];
@@ -586,18 +589,7 @@ __device__ __noinline__ LRootOut l_root_out(const float* ms, float* sm, const LL
     float* mo = sm + C::mbo + C::MBOW * lb.out_mbox;
     float* qpos = sm + C::qpos;
     const float* qvel = sm + C::qvel;
-    if (flags & LF_GOUT) {      // old rotation columns (FK rows of the last forward pass)
-      const float* rt = sm + C::root;
-      S6 a = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
-#pragma unroll
-      for (int k = 0; k < 6; k++) {
-        S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
-                       : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
-        float qdd = rt[36 + k] - dot6(l_arr6(rt + 6 * k), a);
-        a = a + qdd * S;
-      }
-      l_mbo_put_acc(mo, a);
-    }
+    if (flags & LF_GOUT) l_mbo_put_acc(mo, ld6(sm + C::root + LRT_A));   // stable-PD acceleration of the root, solved at the end of the inward sweep
     if (flags & LF_FK) {
       LPose P;
       P.q.w = qpos[3]; P.q.x = qpos[4]; P.q.y = qpos[5]; P.q.z = qpos[6];
@@ -694,13 +686,20 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
         float Rp[9], row[12];
         q2mat(P.q, Rp);
         V3 x = P.x + mrot(Rp, ld3(lb.bpos));
-        Q4 qb; qb.w = lb.bquat[0]; qb.x = lb.bquat[1]; qb.y = lb.bquat[2]; qb.z = lb.bquat[3];
-        Q4 qc = qmul(P.q, qb);
+        const bool xyz = H.axes_xyz != 0;     // warp-uniform: identity body quaternion, hinge axes x, y, z (SMPL family)
+        Q4 qc = P.q;
+        if (!xyz) { Q4 qb; qb.w = lb.bquat[0]; qb.x = lb.bquat[1]; qb.y = lb.bquat[2]; qb.z = lb.bquat[3]; qc = qmul(P.q, qb); }
         S6 v = P.v, ab = P.ab, pa = P.pa;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-          V3 al = ld3(lb.axis + 3 * k);
-          V3 a = qrot(qc, al);
+          V3 al = xyz ? v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f) : ld3(lb.axis + 3 * k);
+          V3 a;
+          if (xyz) {   // column k of the rotation matrix of the running quaternion
+            const float qw = qc.w, qx = qc.x, qy = qc.y, qz = qc.z;
+            a = (k == 0) ? v3(Rp[0], Rp[3], Rp[6])
+              : (k == 1) ? v3(2.f * (qx * qy - qw * qz), 1.f - 2.f * (qx * qx + qz * qz), 2.f * (qy * qz + qw * qx))
+                         : v3(2.f * (qx * qz + qw * qy), 2.f * (qy * qz - qw * qx), 1.f - 2.f * (qx * qx + qy * qy));
+          } else a = qrot(qc, al);
           row[3 * k] = a.x; row[3 * k + 1] = a.y; row[3 * k + 2] = a.z;
           if (flags & LF_VEL) {
             S6 S = s6(a, cross(x, a));
@@ -711,8 +710,16 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
           }
           float sn, cs;
           l_sincos(0.5f * (k == 0 ? q0 : k == 1 ? q1 : q2), &sn, &cs);
-          Q4 qj; qj.w = cs; qj.x = al.x * sn; qj.y = al.y * sn; qj.z = al.z * sn;
-          qc = qmul(qc, qj);
+          if (xyz) {   // qc * (cs, sn e_k)
+            Q4 r;
+            if (k == 0) { r.w = qc.w * cs - qc.x * sn; r.x = qc.w * sn + qc.x * cs; r.y = qc.y * cs + qc.z * sn; r.z = qc.z * cs - qc.y * sn; }
+            else if (k == 1) { r.w = qc.w * cs - qc.y * sn; r.x = qc.x * cs - qc.z * sn; r.y = qc.w * sn + qc.y * cs; r.z = qc.z * cs + qc.x * sn; }
+            else { r.w = qc.w * cs - qc.z * sn; r.x = qc.x * cs + qc.y * sn; r.y = qc.y * cs - qc.x * sn; r.z = qc.w * sn + qc.z * cs; }
+            qc = r;
+          } else {
+            Q4 qj; qj.w = cs; qj.x = al.x * sn; qj.y = al.y * sn; qj.z = al.z * sn;
+            qc = qmul(qc, qj);
+          }
         }
         qc = qnormalize(qc);
         row[9] = x.x; row[10] = x.y; row[11] = x.z;
@@ -1012,9 +1019,9 @@ __device__ __noinline__ bool l_root_in(const float* ms, float* sm, const LLane& 
   const LBody& lb = l_bodies(ms)[0];
   S6 p = l_rec_ld_pb<C>(w, sm, 0, 0);
   bool dirty = false;
+  float* rt = sm + C::root;
   if (need && w.li == 0) {
     float* br = sm + C::body;
-    float* rt = sm + C::root;
     float A[21], r10[10];
     const int ci = l_ld_r10(br, r10);
     rb_expand(r10, A);
@@ -1048,29 +1055,50 @@ __device__ __noinline__ bool l_root_in(const float* ms, float* sm, const LLane& 
       q = qnormalize(q);
       qpos[3] = q.w; qpos[4] = q.x; qpos[5] = q.y; qpos[6] = q.z;
     }
-    // free joint: S_k = (0, e_k) for the translations, (column k-3 of R, 0) for the rotations -> U is a column of A or a
-    // product with its angular block only
-#pragma unroll
-    for (int k = 5; k >= 0; k--) {
-      float Uv[6], D = H.rarm[k], uu;
-      if (k < 3) {
-#pragma unroll
-        for (int i = 0; i < 6; i++) Uv[i] = A[sidx(i, 3 + k)];
-        D += Uv[3 + k];
-        uu = -(k == 0 ? p.l.x : k == 1 ? p.l.y : p.l.z);
-      } else {
-        const V3 c = ld3(br + LBR_AX + 3 * (k - 3));
-#pragma unroll
-        for (int i = 0; i < 6; i++) Uv[i] = fmaf(A[sidx(i, 0)], c.x, fmaf(A[sidx(i, 1)], c.y, A[sidx(i, 2)] * c.z));
-        D += fmaf(c.x, Uv[0], fmaf(c.y, Uv[1], c.z * Uv[2]));
-        uu = -dot(c, p.a);
+    // free joint: S = [0 R ; I 0] is orthonormal, so eliminating its six dofs = solving (A + S diag(armature) S^T) a = -p for the
+    // root's spatial acceleration; the joint accelerations are S^T a (l_root_acc).  System -> shared memory, solved by the lanes below.
+    {
+      const float ar = H.rarm[3], as = H.rarm[4], at = H.rarm[5];
+      A[sidx(3, 3)] += H.rarm[0]; A[sidx(4, 4)] += H.rarm[1]; A[sidx(5, 5)] += H.rarm[2];
+      if (ar != 0.f || as != 0.f || at != 0.f) {
+        const V3 c0 = ld3(br + LBR_AX), c1 = ld3(br + LBR_AX + 3), c2 = ld3(br + LBR_AX + 6);
+        A[sidx(0, 0)] += ar * c0.x * c0.x + as * c1.x * c1.x + at * c2.x * c2.x; A[sidx(0, 1)] += ar * c0.x * c0.y + as * c1.x * c1.y + at * c2.x * c2.y;
+        A[sidx(0, 2)] += ar * c0.x * c0.z + as * c1.x * c1.z + at * c2.x * c2.z; A[sidx(1, 1)] += ar * c0.y * c0.y + as * c1.y * c1.y + at * c2.y * c2.y;
+        A[sidx(1, 2)] += ar * c0.y * c0.z + as * c1.y * c1.z + at * c2.y * c2.z; A[sidx(2, 2)] += ar * c0.z * c0.z + as * c1.z * c1.z + at * c2.z * c2.z;
       }
-      float di = l_rcp(D);
-      sym_rank1(A, Uv, di);
-      p = p + (uu * di) * l_arr6(Uv);
+      float4* r4 = (float4*)rt;
+      r4[0] = make_float4(A[0], A[1], A[2], A[3]); r4[1] = make_float4(A[4], A[5], A[6], A[7]); r4[2] = make_float4(A[8], A[9], A[10], A[11]);
+      r4[3] = make_float4(A[12], A[13], A[14], A[15]); r4[4] = make_float4(A[16], A[17], A[18], A[19]);
+      r4[5] = make_float4(A[20], p.a.x, p.a.y, p.a.z); r4[6] = make_float4(p.l.x, p.l.y, p.l.z, 0.f);
+    }
+  }
+  __syncwarp();
+  {
+    // Gauss-Jordan across the lanes of the env (symmetric positive definite: no pivoting): lane j < 6 holds column j, lane 6 the
+    // right-hand side -p; after the six pivots lane 6 holds the root's spatial acceleration.  Every lane runs it (warp collectives).
+    const bool need_env = __shfl_sync(L_FULL, need ? 1 : 0, w.gbase) != 0;
+    const int j = w.li;
+    float col[6];
 #pragma unroll
-      for (int j = 0; j < 6; j++) rt[6 * k + j] = Uv[j] * di;
-      rt[36 + k] = uu * di;
+    for (int i = 0; i < 6; i++) {
+      const int lo = i < j ? i : j, hi = i < j ? j : i;                 // sidx(i, j) with a run-time column
+      const int ix = (j < 6) ? (lo * (13 - lo)) / 2 + (hi - lo) : 21 + i;
+      const float v = (need_env && j < 7) ? rt[ix] : (i == j ? 1.f : 0.f);
+      col[i] = (j == 6) ? -v : v;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      float m[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) m[i] = __shfl_sync(L_FULL, col[i], w.gbase + k);   // column k (lives in lane k); m[k] = the pivot
+      const float r = col[k] * l_rcp(m[k]);
+#pragma unroll
+      for (int i = 0; i < 6; i++) if (i != k) col[i] = fmaf(-m[i], r, col[i]);
+      col[k] = r;
+    }
+    if (need_env && j == 6) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) rt[LRT_A + i] = col[i];
     }
   }
   __syncwarp();
@@ -1180,23 +1208,18 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
   st_ = st;
 }
 
-// root body of the acceleration sweep: the six free-joint accelerations from the stored factors (into the root's out-mailbox)
+// root body of the acceleration sweep: the spatial acceleration solved at the end of the inward sweep (l_root_in) -> the six
+// free-joint accelerations S^T a, the root's out-mailbox, residuals of the root's contact rows
 template <class C>
 __device__ __noinline__ void l_root_acc(const float* ms, float* sm, const LLane& w, bool run, float* qout, bool* same) {
   const LHdr& H = l_hdr<C>(ms);
   const LBody& lb = l_bodies(ms)[0];
   if (run && w.li == 0) {
-    const float* rt = sm + C::root;
     const float* br = sm + C::body;
-    S6 a = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-      S6 S = (k < 3) ? s6(v3(0.f, 0.f, 0.f), v3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f))
-                     : s6(ld3(br + LBR_AX + 3 * (k - 3)), v3(0.f, 0.f, 0.f));
-      float qdd = rt[36 + k] - dot6(l_arr6(rt + 6 * k), a);
-      qout[k] = qdd;
-      a = a + qdd * S;
-    }
+    const V3 c0 = ld3(br + LBR_AX), c1 = ld3(br + LBR_AX + 3), c2 = ld3(br + LBR_AX + 6);   // rotation columns = axes of the three rotational dofs
+    const S6 a = ld6(sm + C::root + LRT_A);
+    st3(qout, a.l);
+    qout[3] = dot(c0, a.a); qout[4] = dot(c1, a.a); qout[5] = dot(c2, a.a);
     l_mbo_put_acc(sm + C::mbo + C::MBOW * lb.out_mbox, a);
     const int ci = ((const int*)br)[LBR_CI];
     *same = l_rows_eval<C>(H, sm, w, ci & 255, (ci >> 8) & 255, a) && *same;
@@ -1207,16 +1230,14 @@ __device__ __noinline__ void l_root_acc(const float* ms, float* sm, const LLane&
 
 // ------------------------------------------------------------------ S3: outward sweep of the accelerations + residuals of the constraint rows
 // qdd -> qacc (no iterate yet) or qstar (trial point of the line search); rs = J a - aref of every row; returns "the sign pattern
-// of the rows equals the working set" for this lane's env.  first: also derive rc_bits from dirty_bits.
+// of the rows equals the working set" for this lane's env.
 template <class C>
-__device__ __noinline__ bool l_sweep_acc(const float* ms, float* sm, const LLane& w, bool run, bool to_qstar, bool first, LSolveLane& st_) {
+__device__ __noinline__ bool l_sweep_acc(const float* ms, float* sm, const LLane& w, bool run, bool to_qstar) {
   const LHdr& H = l_hdr<C>(ms);
   const LBody* MB = l_bodies(ms);
-  LSolveLane st = st_;
   S6 ca = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
-  bool crc = false, same = true;
+  bool same = true;
   float* qout = sm + (to_qstar ? C::qstar : C::qacc);
-  if (first) st.rc_bits = (st.dirty_bits & 1u);   // the root (step 0, lane 0) is recomputed iff it is dirty
   const bool stepbar = (H.align & 16) && w.bar;
   if (stepbar) __syncthreads();
   l_root_acc<C>(ms, sm, w, run, qout, &same);
@@ -1229,7 +1250,7 @@ __device__ __noinline__ bool l_sweep_acc(const float* ms, float* sm, const LLane
     if (actv) {
       const LBody& lb = MB[b];
       const float* br = sm + C::body + C::BODYW * b;
-      if (!(lb.flags & LB_CARRY_OUT)) { ca = l_mbo_get_acc(sm + C::mbo + C::MBOW * lb.pmbox); crc = false; }
+      if (!(lb.flags & LB_CARRY_OUT)) ca = l_mbo_get_acc(sm + C::mbo + C::MBOW * lb.pmbox);
       S6 a = ca;
       float qdd3[3];
       const LAxes AX = l_ld_axes(br);
@@ -1255,16 +1276,21 @@ __device__ __noinline__ bool l_sweep_acc(const float* ms, float* sm, const LLane
         le[LLE_RS] = rs;
         if ((rs < 0.f ? 1 : 0) != (((const int*)le)[LLE_FLAG] & 1)) same = false;
       }
-      if (first) {
-        bool rc = ((st.dirty_bits >> t) & 1u) || ((lb.flags & LB_CARRY_OUT) && crc);
-        crc = rc;
-        if (rc) st.rc_bits |= 1u << t;
-      }
     }
     __syncwarp();
   }
-  st_ = st;
   return l_gall(same || !run, w);
+}
+
+// after the first inward sweep of a substep (dirty_bits set): rc_bits = what the re-sweeps recompute: the dirty bodies and the bodies
+// that hand their result to one in registers (LHdr::carry_mask)
+template <class C>
+__device__ __forceinline__ void l_solve_plan(const float* ms, const LLane& w, LSolveLane& st) {
+  const LHdr& H = l_hdr<C>(ms);
+  const unsigned cm = H.carry_mask[w.li];
+  unsigned rc = st.dirty_bits;
+  for (int t = 1; t < H.T; t++) if (((cm >> t) & 1u) && ((rc >> (t - 1)) & 1u)) rc |= 1u << t;
+  st.rc_bits = rc;
 }
 
 // ------------------------------------------------------------------ row-space passes of the exact line search (lane-parallel over the row lists)
@@ -1273,9 +1299,11 @@ __device__ __noinline__ bool l_sweep_acc(const float* ms, float* sm, const LLane
 // op 1: sums   (g1 += d phi ; g2 += d (phis - phi) ; s1, s2 at step al)
 // op 2: apply  (phi += al (phis - phi) ; r += al d ; set := (r < 0))
 // op 3: take   (set unchanged at the trial point: r := rs, phi := -D rs on the set)        [fin with an iterate: bookkeeping only]
+// op 4: sums at al = 0 and at al = 1 in one pass: out = g1, g2, s1(0), s1(1), s2(1)   (start of the line search)
 template <class C>
 __device__ __noinline__ void l_rows(float* sm, const LLane& w, bool run, int op, float al, float* out4) {
-  float g1 = 0.f, g2 = 0.f, s1 = 0.f, s2 = 0.f;
+  float g1 = 0.f, g2 = 0.f, s1 = 0.f, s2 = 0.f, s10 = 0.f;
+  if (op == 4) al = 1.f;
   if (run) {
     const int ncon = ((const int*)sm)[C::misc + LMI_NCON], nlim = ((const int*)sm)[C::misc + LMI_NLIM];
     for (int c = w.li; c < ncon; c += LM_LPE) {
@@ -1290,13 +1318,14 @@ __device__ __noinline__ void l_rows(float* sm, const LLane& w, bool run, int op,
         if (op == 0) { ce[LCE_PHI + k] = phs; ce[LCE_R + k] = rs; if (rs < 0.f) nf |= 2 << k; }
         else {
           float r = ce[LCE_R + k], d = rs - r, ph = ce[LCE_PHI + k], v = fmaf(al, d, r);
-          if (op == 1) {
+          if (op == 1 || op == 4) {
             g1 = fmaf(d, ph, g1); g2 = fmaf(d, phs - ph, g2);
             if (v < 0.f) { s1 = fmaf(D * v, d, s1); s2 = fmaf(D * d, d, s2); }
+            if (op == 4 && r < 0.f) s10 = fmaf(D * r, d, s10);
           } else { ce[LCE_PHI + k] = fmaf(al, phs - ph, ph); ce[LCE_R + k] = v; if (v < 0.f) nf |= 2 << k; }
         }
       }
-      if (op != 1) ((int*)ce)[LCE_INFO] = (info & ~30) | nf;
+      if (op != 1 && op != 4) ((int*)ce)[LCE_INFO] = (info & ~30) | nf;
     }
     for (int e = w.li; e < nlim; e += LM_LPE) {
       float* le = sm + C::lim + C::LIMW * e;
@@ -1305,14 +1334,15 @@ __device__ __noinline__ void l_rows(float* sm, const LLane& w, bool run, int op,
       if (op == 0) { le[LLE_PHI] = phs; le[LLE_R] = rs; ((int*)le)[LLE_FLAG] = rs < 0.f ? 1 : 0; }
       else {
         float r = le[LLE_R], d = rs - r, ph = le[LLE_PHI], v = fmaf(al, d, r);
-        if (op == 1) {
+        if (op == 1 || op == 4) {
           g1 = fmaf(d, ph, g1); g2 = fmaf(d, phs - ph, g2);
           if (v < 0.f) { s1 = fmaf(D * v, d, s1); s2 = fmaf(D * d, d, s2); }
+          if (op == 4 && r < 0.f) s10 = fmaf(D * r, d, s10);
         } else { le[LLE_PHI] = fmaf(al, phs - ph, ph); le[LLE_R] = v; ((int*)le)[LLE_FLAG] = v < 0.f ? 1 : 0; }
       }
     }
   }
-  out4[0] = g1; out4[1] = g2; out4[2] = s1; out4[3] = s2;
+  out4[0] = g1; out4[1] = g2; out4[2] = s1; out4[3] = s2; out4[4] = s10;
 }
 
 #ifdef SMPLSIM_STATS
@@ -1336,7 +1366,8 @@ __device__ __noinline__ bool l_linsolve(const float* ms, float* sm, const LLane&
   const LHdr& H = l_hdr<C>(ms);
   if (!C::SELFCOL) {   // no geom-geom rows compiled in: the plain ABA pair
     l_sweep_in<C>(ms, sm, w, run, inflags, st);
-    return l_sweep_acc<C>(ms, sm, w, run, to_qstar, first, st);
+    if (first) l_solve_plan<C>(ms, w, st);
+    return l_sweep_acc<C>(ms, sm, w, run, to_qstar);
   }
   const bool hs = run && H.cfg.self_collision && ((const int*)sm)[C::misc + LMI_NSELF] > 0;
   const bool anyhs = __any_sync(L_FULL, hs);
@@ -1356,7 +1387,8 @@ __device__ __noinline__ bool l_linsolve(const float* ms, float* sm, const LLane&
   }
   if (anyhs) __syncwarp();
   l_sweep_in<C>(ms, sm, w, run, inflags, st);
-  bool same = l_sweep_acc<C>(ms, sm, w, run, to_qstar, first, st);
+  if (first) l_solve_plan<C>(ms, w, st);
+  bool same = l_sweep_acc<C>(ms, sm, w, run, to_qstar);
   if (!anyhs) return same;
   const int rflags = H.dirtypath ? LI_RESWEEP : 0;
   float r0[L_SELFQ], Dr[L_SELFQ], pscale[L_SELFQ];
@@ -1384,7 +1416,7 @@ __device__ __noinline__ bool l_linsolve(const float* ms, float* sm, const LLane&
       if (prb && w.li == lj) eb[qj][LSB_LAM + krow[qj]] = Pj;
       __syncwarp();
       l_sweep_in<C>(ms, sm, w, prb, rflags, st);
-      l_sweep_acc<C>(ms, sm, w, prb, to_qstar, false, st);
+      l_sweep_acc<C>(ms, sm, w, prb, to_qstar);
       float v[L_SELFQ];
       l_self_fix<C>(sm, w, prb, v);
 #pragma unroll
@@ -1447,7 +1479,7 @@ __device__ __noinline__ bool l_linsolve(const float* ms, float* sm, const LLane&
   }
   __syncwarp();
   l_sweep_in<C>(ms, sm, w, hs, rflags, st);
-  const bool same2 = l_sweep_acc<C>(ms, sm, w, hs, to_qstar, false, st);
+  const bool same2 = l_sweep_acc<C>(ms, sm, w, hs, to_qstar);
   float rsf[L_SELFQ];
   l_self_fix<C>(sm, w, hs, rsf);
   bool okrow = true;
@@ -1517,7 +1549,7 @@ __device__ __noinline__ int l_solve(const float* ms, float* sm, const LLane& w, 
   const bool cu = (H.align & 8) && w.bar;
   if (!(cu ? (__syncthreads_or(run) != 0) : __any_sync(L_FULL, run))) return 0;
   // envs whose first trial point changed the sign pattern: adopt it as the iterate, then iterate
-  float o4[4];
+  float o4[5];
   l_rows<C>(sm, w, run, 0, 0.f, o4);
   __syncwarp();
   int it = 1, iters = 0;
@@ -1526,15 +1558,18 @@ __device__ __noinline__ int l_solve(const float* ms, float* sm, const LLane& w, 
     bool same = l_linsolve<C>(ms, sm, w, run, H.dirtypath ? LI_RESWEEP : 0, true, false, st);      // qdd -> qstar
     bool fin = run && same, lsrch = run && !same;
     if (__any_sync(L_FULL, lsrch)) {   // exact line search between the iterate (qacc, r, phi) and the trial point (qstar, rs), row space only
-      l_rows<C>(sm, w, lsrch, 1, 0.f, o4);
-      float g1 = l_gsum(o4[0]), g2 = l_gsum(o4[1]), s1 = l_gsum(o4[2]), s2;
+      l_rows<C>(sm, w, lsrch, 4, 0.f, o4);      // sums at the iterate (al = 0) and at the trial point (al = 1) in one pass over the rows
+      float g1 = l_gsum(o4[0]), g2 = l_gsum(o4[1]), s1 = l_gsum(o4[4]), s11 = l_gsum(o4[2]), s2 = l_gsum(o4[3]);
       float f0 = g1 + s1, al = 0.f, lo = 0.f, hi = -1.f, tol = H.ls_tol * fabsf(f0);
       bool searching = lsrch && (f0 < -L_LS_NOISE * (fabsf(g1) + fabsf(s1)));   // |f0| below the fp32 cancellation floor: converged
       if (searching) al = 1.f;
+      s1 = s11;
       for (int ls = 0; ls < L_LS_MAXITER; ls++) {
         if (!__any_sync(L_FULL, searching)) break;
-        l_rows<C>(sm, w, searching, 1, al, o4);
-        s1 = l_gsum(o4[2]); s2 = l_gsum(o4[3]);
+        if (ls > 0) {
+          l_rows<C>(sm, w, searching, 1, al, o4);
+          s1 = l_gsum(o4[2]); s2 = l_gsum(o4[3]);
+        }
         if (searching) {
           float f = g1 + al * g2 + s1, fp = g2 + s2;
           if (fabsf(f) <= tol) searching = false;
@@ -1561,6 +1596,16 @@ __device__ __noinline__ int l_solve(const float* ms, float* sm, const LLane& w, 
   if (run) { iters = it; *hit_max = true; }
 #ifdef SMPLSIM_STATS
   if (w.live && w.li == 0 && iters > 0) L_STAT(2 + (iters > 6 ? 6 : iters), 1);
+  if (w.live && w.li == 0 && any_rows) {   // [28] env-substeps with >= 3 extra solves, [29] ... that hold a contact new this substep, [30] env-substeps with a new contact, [31] contacts of [28]
+    const int ncon = ((const int*)sm)[C::misc + LMI_NCON];
+    int hasnew = 0, np = 0;
+    for (int c = 0; c < ncon; c++) {
+      int info = ((const int*)l_centry<C>(sm, w, c))[LCE_INFO];
+      if (info & 1) { np++; if (info & 32) hasnew = 1; }
+    }
+    if (hasnew) L_STAT(30, 1);
+    if (iters >= 3) { L_STAT(28, 1); if (hasnew) L_STAT(29, 1); L_STAT(31, np); }
+  }
   if (w.live && w.li == 0) {   // [16] rows, [17] inherit guess wrong vs the final set, [18] prediction wrong, [19] both wrong, [20] contacts where inherit is right, [21] pred right
     const int ncon = ((const int*)sm)[C::misc + LMI_NCON];
     for (int c = 0; c < ncon; c++) {

@@ -30,7 +30,7 @@ struct LHdr {
   int nb, nv, nu, ng, nslot, T, nmbi, nmbo;
   int obs_dim, self_obs_dim, warmset, dirtypath;
   int bytes, body_off, geom_off, align;
-  int pair_off, npair, pad5[2];                 // capsule / sphere geom pairs MuJoCo would collide (LPair array)       // image size and the byte offsets of the LBody / LGeom arrays
+  int pair_off, npair, axes_xyz, pad5;          // axes_xyz: every non-root body has the identity body quaternion and hinge axes x, y, z (the SMPL family's MJCF): FK takes the axes from rotation-matrix columns                 // capsule / sphere geom pairs MuJoCo would collide (LPair array)       // image size and the byte offsets of the LBody / LGeom arrays
   float ls_tol, margin, mu, impratio;
   float solimp[5], imp_a, imp_b, K;
   float B, h, grav[3], plane_pos[3];
@@ -43,6 +43,7 @@ struct LHdr {
   unsigned char step_nmb[LM_TMAX];             // per step: max mailbox children
   unsigned char step_root[LM_TMAX];            // 1: this step holds the root body (free joint, 6 dofs)
   unsigned char pad3[LM_TMAX];
+  unsigned carry_mask[LM_LPE];                 // per lane: bit t = the body of (step t, lane) takes its parent's state in registers (LB_CARRY_OUT)
 };
 
 struct LBody {   // 72 words
@@ -197,6 +198,16 @@ static inline std::string lane_build(const SmplsimModelDesc* s, const SmplsimEnv
     P.mb[P.nmb++] = (signed char)B[b].in_mbox;
   }
   H.nmbi = nmbi; H.nmbo = nmbo;
+  H.axes_xyz = 1;
+  for (int b = 1; b < nb; b++) {
+    const LBody& L = B[b];
+    if (L.bquat[0] != 1.f || L.bquat[1] != 0.f || L.bquat[2] != 0.f || L.bquat[3] != 0.f) H.axes_xyz = 0;
+    for (int k = 0; k < 3; k++) for (int j = 0; j < 3; j++) if (L.axis[3 * k + j] != (k == j ? 1.f : 0.f)) H.axes_xyz = 0;
+  }
+  for (int l = 0; l < LM_LPE; l++) {
+    H.carry_mask[l] = 0u;
+    for (int tt = 1; tt < H.T; tt++) { int b = H.sched[tt][l]; if (b >= 0 && (B[b].flags & LB_CARRY_OUT)) H.carry_mask[l] |= 1u << tt; }
+  }
   // ---- geoms (grouped per body) and their contact slots
   int ns = 0;
   H.legal_mask = 1ull;

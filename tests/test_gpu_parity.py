@@ -540,10 +540,10 @@ def test_env_step_with_self_collision_matches_oracle(backend):
             assert bool(term[i]) == te and bool(trunc[i]) == tr
 
 
-@pytest.mark.parametrize("knob", ["SMPLSIM_REC=smem", "SMPLSIM_ALIGN=0", "SMPLSIM_DIRTYPATH=0", "SMPLSIM_WPB=3"])
+@pytest.mark.parametrize("knob", ["SMPLSIM_REC=smem", "SMPLSIM_ALIGN=0", "SMPLSIM_DIRTYPATH=0", "SMPLSIM_WPB=3", "SMPLSIM_AXES=generic"])
 def test_every_runtime_knob_keeps_parity(backend, knob, monkeypatch):
     """The debug / A-B switches that stay selectable are read at smplsim_create: lane records in shared memory
-    instead of tensor memory, no CTA phase-alignment barriers, full instead of dirty-chain re-sweeps, a forced CTA size.  Each must
+    instead of tensor memory, no CTA phase-alignment barriers, full instead of dirty-chain re-sweeps, a forced CTA size, FK through the general hinge-axis path.  Each must
     give the same physics: one substep from contact states + two env steps, against the oracle."""
     k, v = knob.split("=")
     monkeypatch.setenv(k, v)

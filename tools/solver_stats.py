@@ -33,3 +33,4 @@ print(f"contacts {s[13]} (new {s[14]});  rows predicted active but free {s[9]}, 
 print(f"rows {s[16]}: inherit wrong {s[17]} ({s[17] / max(1, s[16]):.3f}), prediction wrong {s[18]} ({s[18] / max(1, s[16]):.3f}), both wrong {s[19]}; contacts with exact inherit {s[20]}, exact prediction {s[21]} of {s[13]}")
 miss = s[1] - s[2]
 print(f"first-pass misses {miss}: every flipped row below 1e-3 N: {s[22]}, 1e-2 N: {s[23]}, 0.1 N: {s[24]}, 1 N: {s[25]}; below 1e-4 / 1e-3 of the total contact force: {s[26]} / {s[27]}")
+print(f"env-substeps with >= 3 extra solves: {s[28]} (of which with a contact new this substep: {s[29]}; mean contacts {s[31] / max(1, s[28]):.1f} vs {s[13] / max(1, s[1]):.1f} overall); env-substeps with a new contact: {s[30]}")
