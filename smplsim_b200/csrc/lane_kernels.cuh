@@ -124,7 +124,7 @@ struct LLane {
 };
 
 template <class C> __device__ __forceinline__ const LHdr& l_hdr(const float* ms) { return *(const LHdr*)ms; }
-__device__ __forceinline__ const LBody* l_bodies(const float* ms) { return (const LBody*)((const char*)ms + ((const LHdr*)ms)->body_off); }
+__device__ __forceinline__ const LBody* l_bodies(const float* ms) { return (const LBody*)((const char*)ms + LM_BODY_OFF); }
 __device__ __forceinline__ const LGeom* l_geoms(const float* ms) { return (const LGeom*)((const char*)ms + ((const LHdr*)ms)->geom_off); }
 
 __device__ __forceinline__ float l_gsum(float v) {

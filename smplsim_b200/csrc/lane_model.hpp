@@ -7,6 +7,7 @@
 // goes through a small shared-memory mailbox.  One image per handle lives in global memory; each CTA stages it into
 // shared memory once (bulk copy).
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -29,8 +30,9 @@
 struct LHdr {
   int nb, nv, nu, ng, nslot, T, nmbi, nmbo;
   int obs_dim, self_obs_dim, warmset, dirtypath;
-  int bytes, body_off, geom_off, align;
-  int pair_off, npair, axes_xyz, pad5;          // axes_xyz: every non-root body has the identity body quaternion and hinge axes x, y, z (the SMPL family's MJCF): FK takes the axes from rotation-matrix columns                 // capsule / sphere geom pairs MuJoCo would collide (LPair array)       // image size and the byte offsets of the LBody / LGeom arrays
+  int bytes, body_off, geom_off, align;         // image size, byte offsets of the LBody (== LM_BODY_OFF) / LGeom arrays, CTA alignment bits
+  int pair_off, npair, axes_xyz, pad5;          // capsule / sphere geom pairs MuJoCo would collide (LPair array at pair_off); axes_xyz: every non-root
+                                                // body has the identity body quaternion and hinge axes x, y, z (the SMPL family's MJCF)
   float ls_tol, margin, mu, impratio;
   float solimp[5], imp_a, imp_b, K;
   float B, h, grav[3], plane_pos[3];
@@ -61,6 +63,8 @@ struct LBody {   // 72 words
   int pad1[2];
 };
 
+#define LM_BODY_OFF ((sizeof(LHdr) + 15) & ~(size_t)15)   // byte offset of the LBody array in the image (compile-time: the kernels add no header load)
+
 struct LGeom {   // 20 words
   float pos[3], pad0;
   float size[3], pad1;
@@ -69,7 +73,6 @@ struct LGeom {   // 20 words
 };
 
 struct LPair { short g1, g2; };   // geom indices, g1 < g2
-
 struct LaneImage {
   std::vector<unsigned char> bytes;
   LHdr* hdr() { return (LHdr*)bytes.data(); }
@@ -119,7 +122,7 @@ static inline std::string lane_build(const SmplsimModelDesc* s, const SmplsimEnv
       }
     }
   }
-  size_t body_off = (sizeof(LHdr) + 15) & ~(size_t)15, geom_off = body_off + sizeof(LBody) * nb;
+  size_t body_off = LM_BODY_OFF, geom_off = body_off + sizeof(LBody) * nb;
   size_t pair_off = (geom_off + sizeof(LGeom) * ng + 15) & ~(size_t)15;
   size_t total = (pair_off + sizeof(LPair) * pairs.size() + 15) & ~(size_t)15;
   out.bytes.assign(total, 0);

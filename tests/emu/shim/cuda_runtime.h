@@ -44,6 +44,8 @@ struct dim3 {
 struct float4 { float x, y, z, w; };
 struct float2 { float x, y; };
 struct uint4 { unsigned x, y, z, w; };
+struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 
 typedef int cudaError_t;
