@@ -219,9 +219,9 @@ static inline float __uint_as_float(unsigned u) { return emu_float(u); }
 // K (3 x 6) and c (3) of the body this lane runs at step t.  Tensor-memory accesses are warp collectives: every lane of the
 // warp must reach them (callers keep them outside lane-divergent code); `keep` lanes write back what is there.
 template <class C>
-__device__ __forceinline__ void l_rec_ld_Kc(const LLane& w, float* sm, int t, int b, float* K, float* c) {
+__device__ __forceinline__ void l_rec_ld_Kc(const unsigned tm, float* sm, int t, int b, float* K, float* c) {
   if (C::RECT) {
-    unsigned r[20], a = w.tm + (unsigned)(C::RECW * t);
+    unsigned r[20], a = tm + (unsigned)(C::RECW * t);
     L_TM_LD16(a, r);
     L_TM_LD4(a + 16u, r + 16);
     c[2] = (b >= 0) ? sm[C::body + C::BODYW * b + LBR_C2] : 0.f;
@@ -239,9 +239,9 @@ __device__ __forceinline__ void l_rec_ld_Kc(const LLane& w, float* sm, int t, in
 }
 // Stores are not waited for here: the sweeps end with one tcgen05.wait::st (a record is read again in a later sweep only).
 template <class C>
-__device__ __forceinline__ void l_rec_st_Kc(const LLane& w, float* sm, int t, int b, const float* K, const float* c, bool wr, bool preload) {
+__device__ __forceinline__ void l_rec_st_Kc(const unsigned tm, float* sm, int t, int b, const float* K, const float* c, bool wr, bool preload) {
   if (C::RECT) {
-    unsigned r[20], a = w.tm + (unsigned)(C::RECW * t);
+    unsigned r[20], a = tm + (unsigned)(C::RECW * t);
     if (preload) {   // some lanes keep their record (clean chains of a re-sweep): read - select - write
       L_TM_LD16(a, r);
       L_TM_LD4(a + 16u, r + 16);
@@ -264,10 +264,10 @@ __device__ __forceinline__ void l_rec_st_Kc(const LLane& w, float* sm, int t, in
   }
 }
 template <class C>
-__device__ __forceinline__ S6 l_rec_ld_pb(const LLane& w, float* sm, int t, int b) {
+__device__ __forceinline__ S6 l_rec_ld_pb(const unsigned tm, float* sm, int t, int b) {
   float q[6];
   if (C::RECT) {
-    unsigned r[8], a = w.tm + (unsigned)(C::RECW * t + 20);
+    unsigned r[8], a = tm + (unsigned)(C::RECW * t + 20);
     L_TM_LD8(a, r);
     L_TM_WAIT_LD();
 #pragma unroll
@@ -280,10 +280,10 @@ __device__ __forceinline__ S6 l_rec_ld_pb(const LLane& w, float* sm, int t, int 
   return s6(v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]));
 }
 template <class C>
-__device__ __forceinline__ void l_rec_st_pb(const LLane& w, float* sm, int t, int b, S6 pb, bool wr) {
+__device__ __forceinline__ void l_rec_st_pb(const unsigned tm, const bool keep, float* sm, int t, int b, S6 pb, bool wr) {
   if (C::RECT) {
-    unsigned r[8], a = w.tm + (unsigned)(C::RECW * t + 20);
-    if (!w.bar) {   // partial re-forward (mj_checkAcc path): the other envs of the warp keep their pb
+    unsigned r[8], a = tm + (unsigned)(C::RECW * t + 20);
+    if (keep) {   // partial re-forward (mj_checkAcc path): the other envs of the warp keep their pb
       L_TM_LD8(a, r);
       L_TM_WAIT_LD();
     }
@@ -581,6 +581,7 @@ __device__ __noinline__ LRootOut l_root_out(const float* ms, float* sm, const LL
   const LHdr& H = l_hdr<C>(ms);
   const LBody& lb = l_bodies(ms)[0];
   LRootOut R; R.ncon = 0; R.npresent = 0; R.gbits = 0ull;
+  const unsigned tm = w.tm;
   const bool actv = w.live && w.li == 0;
   S6 pbv = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
   int alloc = 0;
@@ -620,7 +621,7 @@ __device__ __noinline__ LRootOut l_root_out(const float* ms, float* sm, const LL
       }
     }
   }
-  if (flags & LF_VEL) l_rec_st_pb<C>(w, sm, 0, 0, pbv, actv);
+  if (flags & LF_VEL) l_rec_st_pb<C>(tm, !w.bar, sm, 0, 0, pbv, actv);
   R.ncon = __shfl_sync(L_FULL, alloc, w.gbase);
   __syncwarp();
   return R;
@@ -631,6 +632,10 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
   const LHdr& H = l_hdr<C>(ms);
   const LBody* MB = l_bodies(ms);
   const LGeom* MG = l_geoms(ms);
+  const unsigned tm = w.tm;   // lane fields the loop uses, copied out of the LLane in memory: the tensor-memory statements clobber memory, every w.x after one is a reload from the stack
+  const int li = w.li, T = H.T;
+  const bool live = w.live, keep = !w.bar;
+  const float hh = H.h;
   const float h0 = dot(ld3(H.plane_n), ld3(sm + C::qpos) - ld3(H.plane_pos));
   LRootOut R0 = l_root_out<C>(ms, sm, w, flags, h0);
   LPose P;   // pose / velocity / bias acceleration handed down the lane's chain
@@ -640,12 +645,12 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
   unsigned long long gbits = R0.gbits;
   const bool spd_torque = (flags & LF_GOUT) && H.cfg.control_mode == SMPLSIM_CTRL_UHC_PD;
   const bool stepbar = (H.align & 16) && w.bar;
-  for (int t = 1; t < H.T; t++) {
+  for (int t = 1; t < T; t++) {
     if (stepbar) __syncthreads();
-    const int b = H.sched[t][w.li];
-    const bool actv = w.live && b >= 0;
+    const int b = H.sched[t][li];
+    const bool actv = live && b >= 0;
     float K[18], kc[3];
-    if (flags & LF_GOUT) l_rec_ld_Kc<C>(w, sm, t, b, K, kc);
+    if (flags & LF_GOUT) l_rec_ld_Kc<C>(tm, sm, t, b, K, kc);
     S6 pbv = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
     float* br = sm + C::body + C::BODYW * (actv ? b : 0);
     int alloc = 0, nlr = 0;   // contact entries / limit rows this lane wants
@@ -674,7 +679,7 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
             const int i = d0 + k - 6;
             float q = k == 0 ? q0 : k == 1 ? q1 : q2, qd = k == 0 ? qd0 : k == 1 ? qd1 : qd2;
             float tgt = fmaf(sm[C::act + i], lb.ascale[k], lb.aoffset[k]);
-            float tq = -lb.kp[k] * (q + qd * H.h - tgt) - lb.kd[k] * (qd + qdd * H.h);
+            float tq = -lb.kp[k] * (q + qd * hh - tgt) - lb.kd[k] * (qd + qdd * hh);
             tq = fminf(fmaxf(tq, -lb.tlim[k]), lb.tlim[k]);
             sm[C::tau + i] = ztau ? 0.f : tq;
           }
@@ -774,7 +779,7 @@ __device__ __noinline__ LFkOut l_sweep_out(const float* ms, float* sm, const LLa
         npresent += lcnt;
       }
     }
-    if (flags & LF_VEL) l_rec_st_pb<C>(w, sm, t, b, pbv, actv);
+    if (flags & LF_VEL) l_rec_st_pb<C>(tm, keep, sm, t, b, pbv, actv);
     __syncwarp();
   }
   if (C::RECT && (flags & LF_VEL)) L_TM_WAIT_ST();   // pb is read by the inward sweep that follows
@@ -1017,7 +1022,8 @@ template <class C>
 __device__ __noinline__ bool l_root_in(const float* ms, float* sm, const LLane& w, bool need, int flags) {
   const LHdr& H = l_hdr<C>(ms);
   const LBody& lb = l_bodies(ms)[0];
-  S6 p = l_rec_ld_pb<C>(w, sm, 0, 0);
+  const unsigned tm = w.tm;
+  S6 p = l_rec_ld_pb<C>(tm, sm, 0, 0);
   bool dirty = false;
   float* rt = sm + C::root;
   if (need && w.li == 0) {
@@ -1110,6 +1116,9 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
   const LHdr& H = l_hdr<C>(ms);
   const LBody* MB = l_bodies(ms);
   LSolveLane st = st_;
+  const unsigned tm = w.tm;   // lane fields the loop uses, copied out of the LLane in memory: the tensor-memory statements clobber memory, every w.x after one is a reload from the stack
+  const int li = w.li;
+  const float hh = H.h;
   float cA[21];
 #pragma unroll
   for (int j = 0; j < 21; j++) cA[j] = 0.f;
@@ -1120,15 +1129,12 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
   const bool stepbar = (H.align & 16) && w.bar;
   for (int t = H.T - 1; t >= 1; t--) {
     if (stepbar) __syncthreads();
-    const int b = H.sched[t][w.li];
+    const int b = H.sched[t][li];
     const bool actv = run && b >= 0;
     const bool need = actv && (!resweep || ((st.rc_bits >> t) & 1u));
     if (resweep && !__any_sync(L_FULL, need)) continue;
-    S6 p = l_rec_ld_pb<C>(w, sm, t, b);
-    float K[18], kc[3];
-#pragma unroll
-    for (int j = 0; j < 18; j++) K[j] = 0.f;
-    kc[0] = kc[1] = kc[2] = 0.f;
+    S6 p = l_rec_ld_pb<C>(tm, sm, t, b);
+    float K[18], kc[3];   // written by the lanes that need the body; the others store back what the record holds (or nothing that is read)
     if (need) {
       const LBody& lb = MB[b];
       float* br = sm + C::body + C::BODYW * b;
@@ -1168,18 +1174,18 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
         float s[6], Uv[6];
         l_s6arr(S, s);
         sym_mul(A, s, Uv);
-        float D = lb.arm[k] + (spd ? H.h * lb.kd[k] : lD[k]);
+        float D = lb.arm[k] + (spd ? hh * lb.kd[k] : lD[k]);
 #pragma unroll
         for (int j = 0; j < 6; j++) D = fmaf(s[j], Uv[j], D);
         float di = l_rcp(D), tin;
         if (spd) {
           float q = sm[C::qpos + d + 1], qd = sm[C::qvel + d];
           if (flags & LI_INTEGRATE) {
-            qd = fmaf(H.h, sm[C::qacc + d], qd); q = fmaf(H.h, qd, q);
+            qd = fmaf(hh, sm[C::qacc + d], qd); q = fmaf(hh, qd, q);
             sm[C::qvel + d] = qd; sm[C::qpos + d + 1] = q;
           }
           float tgt = fmaf(sm[C::act + i], lb.ascale[k], lb.aoffset[k]);
-          tin = -lb.kp[k] * (q + qd * H.h - tgt) - lb.kd[k] * qd;
+          tin = -lb.kp[k] * (q + qd * hh - tgt) - lb.kd[k] * qd;
         } else tin = sm[C::tau + i] + lT[k];
         float uu = tin - dot6(S, p);
         sym_rank1(A, Uv, di);
@@ -1194,7 +1200,7 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
       if (lb.in_mbox >= 0) l_mbi_put(sm + C::mbi + C::MBIW * lb.in_mbox, A, p, dirty);
       if (!spd && !resweep && dirty) st.dirty_bits |= 1u << t;
     }
-    l_rec_st_Kc<C>(w, sm, t, b, K, kc, need, resweep);
+    l_rec_st_Kc<C>(tm, sm, t, b, K, kc, need, resweep);
     __syncwarp();
   }
   {   // the root body closes the sweep
@@ -1202,7 +1208,7 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
     const bool need0 = run && (!resweep || (st.rc_bits & 1u));
     bool d0 = false;
     if (!resweep || __any_sync(L_FULL, need0)) d0 = l_root_in<C>(ms, sm, w, need0, flags);
-    if (!spd && !resweep && d0 && w.li == 0) st.dirty_bits |= 1u;
+    if (!spd && !resweep && d0 && li == 0) st.dirty_bits |= 1u;
   }
   if (C::RECT) L_TM_WAIT_ST();   // the records of this sweep are read by the next one
   st_ = st;
@@ -1239,14 +1245,16 @@ __device__ __noinline__ bool l_sweep_acc(const float* ms, float* sm, const LLane
   bool same = true;
   float* qout = sm + (to_qstar ? C::qstar : C::qacc);
   const bool stepbar = (H.align & 16) && w.bar;
+  const unsigned tm = w.tm;   // lane fields the loop uses, copied out of the LLane in memory: the tensor-memory statements clobber memory, every w.x after one is a reload from the stack
+  const int li = w.li, T = H.T;
   if (stepbar) __syncthreads();
   l_root_acc<C>(ms, sm, w, run, qout, &same);
-  for (int t = 1; t < H.T; t++) {
+  for (int t = 1; t < T; t++) {
     if (stepbar) __syncthreads();
-    const int b = H.sched[t][w.li];
+    const int b = H.sched[t][li];
     const bool actv = run && b >= 0;
     float K[18], kc[3];
-    l_rec_ld_Kc<C>(w, sm, t, b, K, kc);
+    l_rec_ld_Kc<C>(tm, sm, t, b, K, kc);
     if (actv) {
       const LBody& lb = MB[b];
       const float* br = sm + C::body + C::BODYW * b;

@@ -161,7 +161,8 @@ static int create_impl(const SmplsimModelDesc* s, int nmodels, const int32_t* en
   LHdr& H = *h->img.hdr();
   { const char* dp = std::getenv("SMPLSIM_DIRTYPATH"); if (dp) H.dirtypath = std::atoi(dp); }
   { const char* ax = std::getenv("SMPLSIM_AXES"); if (ax && std::string(ax) == "generic") H.axes_xyz = 0; }   // FK through the general hinge-axis path
-  { const char* al = std::getenv("SMPLSIM_ALIGN"); if (al) H.align = std::atoi(al); }   // CTA phase-alignment barriers (bit 0 substep, 1 solve, 2 stable-PD sweep)
+  { const char* al = std::getenv("SMPLSIM_ALIGN"); if (al) H.align = std::atoi(al); }
+  if (H.align & 16) H.align |= 8;   // barriers at every sweep step need CTA-uniform solver iteration counts (else the warps disagree on the number of sweeps: deadlock)   // CTA phase-alignment barriers (bit 0 substep, 1 solve, 2 stable-PD sweep)
   for (int b = 0; b < H.nb; b++) if (h->img.bodies()[b].ngeom > 1) { delete h; return fail(SMPLSIM_EUNSUPPORTED, "more than one geom on a body"); }
   std::vector<LaneImage> more(nmodels > 1 ? nmodels - 1 : 0);   // tables of the other body shapes
   for (int k = 1; k < nmodels; k++) {
