@@ -247,12 +247,12 @@ __device__ __forceinline__ void l_rec_st_Kc(const unsigned tm, float* sm, int t,
       L_TM_LD4(a + 16u, r + 16);
       L_TM_WAIT_LD();
     }
-    if (wr) {
+    if (wr || !preload) {   // without a preload the lanes that do not write hold nothing worth keeping: no per-lane select, the registers of K go out as they are
 #pragma unroll
       for (int i = 0; i < 18; i++) r[i] = __float_as_uint(K[i]);
       r[18] = __float_as_uint(c[0]); r[19] = __float_as_uint(c[1]);
-      if (b >= 0) sm[C::body + C::BODYW * b + LBR_C2] = c[2];
     }
+    if (wr && b >= 0) sm[C::body + C::BODYW * b + LBR_C2] = c[2];
     L_TM_ST16(a, r);
     L_TM_ST4(a + 16u, r + 16);
   } else if (wr && b >= 0) {
