@@ -1018,7 +1018,7 @@ __device__ __noinline__ int l_self_collide(const float* ms, float* sm, const LLa
 // root body of the inward sweep (every lane makes the call; lane 0 of the group works): children arrive through the
 // in-mailboxes; (semi-implicit Euler of the free joint, then) elimination of its six dofs; the factors K (6 x 6), c (6) stay in
 // shared memory.  Returns "the root has constraint rows in its subtree".
-template <class C>
+template <class C, bool SPD>
 __device__ __noinline__ bool l_root_in(const float* ms, float* sm, const LLane& w, bool need, int flags) {
   const LHdr& H = l_hdr<C>(ms);
   const LBody& lb = l_bodies(ms)[0];
@@ -1032,13 +1032,13 @@ __device__ __noinline__ bool l_root_in(const float* ms, float* sm, const LLane& 
     const int ci = l_ld_r10(br, r10);
     rb_expand(r10, A);
     for (int j = 0; j < lb.nmb; j++) dirty = l_mbi_add(sm + C::mbi + C::MBIW * lb.mb[j], A, p) || dirty;
-    if (!(flags & LI_SPD)) {
+    if (!SPD) {
       const int cn = (ci >> 8) & 255;
       dirty = dirty || cn > 0;
       l_fold_contacts<C>(H, sm, w, ci & 255, cn, A, p);
       if (C::SELFCOL && ((const int*)sm)[C::misc + LMI_NSELF]) { l_self_wrench<C>(H, sm, w, 0, p); dirty = dirty || l_self_touches<C>(sm, w, 0); }
     }
-    if (flags & LI_INTEGRATE) {
+    if (SPD && (flags & LI_INTEGRATE)) {
       float* qpos = sm + C::qpos; float* qvel = sm + C::qvel; const float* qacc = sm + C::qacc;
       float* misc = sm + C::misc;
       float h = H.h;
@@ -1111,7 +1111,9 @@ __device__ __noinline__ bool l_root_in(const float* ms, float* sm, const LLane& 
   return dirty;
 }
 
-template <class C>
+// SPD (compile time): the stable-PD system (LI_SPD, optionally LI_INTEGRATE; never a re-sweep) -- the two uses share no flag-dependent code,
+// so each instance carries only its own
+template <class C, bool SPD>
 __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane& w, bool run, int flags, LSolveLane& st_) {
   const LHdr& H = l_hdr<C>(ms);
   const LBody* MB = l_bodies(ms);
@@ -1124,7 +1126,8 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
   for (int j = 0; j < 21; j++) cA[j] = 0.f;
   S6 cp = s6(v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f));
   bool cdirty = false;
-  const bool spd = (flags & LI_SPD) != 0, resweep = (flags & LI_RESWEEP) != 0;
+  constexpr bool spd = SPD;
+  const bool resweep = !SPD && (flags & LI_RESWEEP) != 0;
   if (!resweep && !spd) st.dirty_bits = 0u;
   const bool stepbar = (H.align & 16) && w.bar;
   for (int t = H.T - 1; t >= 1; t--) {
@@ -1207,7 +1210,7 @@ __device__ __noinline__ void l_sweep_in(const float* ms, float* sm, const LLane&
     if (stepbar) __syncthreads();
     const bool need0 = run && (!resweep || (st.rc_bits & 1u));
     bool d0 = false;
-    if (!resweep || __any_sync(L_FULL, need0)) d0 = l_root_in<C>(ms, sm, w, need0, flags);
+    if (!resweep || __any_sync(L_FULL, need0)) d0 = l_root_in<C, SPD>(ms, sm, w, need0, flags);
     if (!spd && !resweep && d0 && li == 0) st.dirty_bits |= 1u;
   }
   if (C::RECT) L_TM_WAIT_ST();   // the records of this sweep are read by the next one
@@ -1373,7 +1376,7 @@ template <class C>
 __device__ __noinline__ bool l_linsolve(const float* ms, float* sm, const LLane& w, bool run, int inflags, bool to_qstar, bool first, LSolveLane& st) {
   const LHdr& H = l_hdr<C>(ms);
   if (!C::SELFCOL) {   // no geom-geom rows compiled in: the plain ABA pair
-    l_sweep_in<C>(ms, sm, w, run, inflags, st);
+    l_sweep_in<C, false>(ms, sm, w, run, inflags, st);
     if (first) l_solve_plan<C>(ms, w, st);
     return l_sweep_acc<C>(ms, sm, w, run, to_qstar);
   }
@@ -1394,7 +1397,7 @@ __device__ __noinline__ bool l_linsolve(const float* ms, float* sm, const LLane&
     }
   }
   if (anyhs) __syncwarp();
-  l_sweep_in<C>(ms, sm, w, run, inflags, st);
+  l_sweep_in<C, false>(ms, sm, w, run, inflags, st);
   if (first) l_solve_plan<C>(ms, w, st);
   bool same = l_sweep_acc<C>(ms, sm, w, run, to_qstar);
   if (!anyhs) return same;
@@ -1423,7 +1426,7 @@ __device__ __noinline__ bool l_linsolve(const float* ms, float* sm, const LLane&
       if (!__any_sync(L_FULL, prb)) continue;
       if (prb && w.li == lj) eb[qj][LSB_LAM + krow[qj]] = Pj;
       __syncwarp();
-      l_sweep_in<C>(ms, sm, w, prb, rflags, st);
+      l_sweep_in<C, false>(ms, sm, w, prb, rflags, st);
       l_sweep_acc<C>(ms, sm, w, prb, to_qstar);
       float v[L_SELFQ];
       l_self_fix<C>(sm, w, prb, v);
@@ -1486,7 +1489,7 @@ __device__ __noinline__ bool l_linsolve(const float* ms, float* sm, const LLane&
     if (valid[q]) eb[q][LSB_LAM + krow[q]] = act[q] ? rhs[q] / d : 0.f;
   }
   __syncwarp();
-  l_sweep_in<C>(ms, sm, w, hs, rflags, st);
+  l_sweep_in<C, false>(ms, sm, w, hs, rflags, st);
   const bool same2 = l_sweep_acc<C>(ms, sm, w, hs, to_qstar);
   float rsf[L_SELFQ];
   l_self_fix<C>(sm, w, hs, rsf);
@@ -1773,7 +1776,7 @@ __device__ __noinline__ void l_substeps(const float* ms, float* sm, const LLane&
     int bad = l_check<C>(ms, sm, w, 0);
     if (spd && !stale) {   // spd_inertia = "fresh": factors of the current state, then the torque
       l_sweep_out<C>(ms, sm, w, LF_FK | LF_VEL, false);
-      l_sweep_in<C>(ms, sm, w, w.live, LI_SPD, st);
+      l_sweep_in<C, true>(ms, sm, w, w.live, LI_SPD, st);
       l_sweep_out<C>(ms, sm, w, LF_GOUT, bad != 0);
     }
     const bool last = (s == nsub - 1);
@@ -1811,7 +1814,7 @@ __device__ __noinline__ void l_substeps(const float* ms, float* sm, const LLane&
     }
     if (last && write_fwd) __syncwarp();   // the integration below overwrites what other lanes are still copying
     if (H.align & 4) __syncthreads();
-    if (spd && stale && (!last || prep_last)) l_sweep_in<C>(ms, sm, w, w.live, LI_SPD | LI_INTEGRATE, st);   // FK rows: s_k ; qpos / qvel: s_{k+1}
+    if (spd && stale && (!last || prep_last)) l_sweep_in<C, true>(ms, sm, w, w.live, LI_SPD | LI_INTEGRATE, st);   // FK rows: s_k ; qpos / qvel: s_{k+1}
     else l_integrate<C>(ms, sm, w, st);
   }
 }
@@ -2128,7 +2131,7 @@ __device__ __noinline__ void l_spd_prologue(const float* ms, float* sm, const LL
   l_copy_in<C>(sm + C::qpos, sta.qpos + eo * (H.nv + 1), H.nv + 1, w);
   l_copy_in<C>(sm + C::qvel, sta.qvel + eo * H.nv, H.nv, w);
   __syncwarp();
-  l_sweep_in<C>(ms, sm, w, w.live, LI_SPD, st);
+  l_sweep_in<C, true>(ms, sm, w, w.live, LI_SPD, st);
 }
 
 template <class C>
@@ -2246,7 +2249,7 @@ __global__ void __launch_bounds__(256, 1) k_reset5(const float* __restrict__ gim
       __syncwarp();
       if (w.live && w.li == 0) ti[L_TSK_RNG] = (int)(base + (uint32_t)ngrp);
       __syncwarp();
-      if (spd_st) l_sweep_in<C>(ms, sm, w, w.live, LI_SPD, st);   // factors of the last forward pass, PD error of the current state and the new action
+      if (spd_st) l_sweep_in<C, true>(ms, sm, w, w.live, LI_SPD, st);   // factors of the last forward pass, PD error of the current state and the new action
       l_substeps<C>(ms, sm, w, c.nsubsteps, 0, &fo, a.st, false, false, st);
     }
   }
