@@ -2044,15 +2044,12 @@ __device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int im
   unsigned* slot = (unsigned*)(smem + img_bytes / 4);   // [0] tensor-memory base, [2..3] mbarrier of the table copy
 #ifndef SMPLSIM_EMU
   {
-    // the constant table arrives as ONE bulk asynchronous copy (TMA engine, cp.async.bulk -> UBLKCP) signalled on an mbarrier,
-    // issued by one thread; it lands while the warps carve their env rows and claim tensor memory
-    const unsigned mb = (unsigned)__cvta_generic_to_shared(slot + 2), dst = (unsigned)__cvta_generic_to_shared(smem);
+    // the constant table arrives as ONE bulk asynchronous copy (TMA engine, cp.async.bulk -> UBLKCP) signalled on an mbarrier: one thread
+    // initialises the barrier here and issues the copy behind the CTA barrier below (init -> fence -> CTA sync -> expect_tx + copy)
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(slot + 2);
     if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((unsigned)img_bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(dst), "l"(gimg), "r"((unsigned)img_bytes), "r"(mb) : "memory");
     }
   }
 #else
@@ -2080,8 +2077,13 @@ __device__ __forceinline__ float* l_setup(const float* __restrict__ gimg, int im
   __syncthreads();
 #ifndef SMPLSIM_EMU
   if (C::RECT) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  {   // every thread waits for the table (phase 0 of the mbarrier)
-    const unsigned mb = (unsigned)__cvta_generic_to_shared(slot + 2);
+  {   // one thread starts the copy; every thread waits for the table (phase 0 of the mbarrier)
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(slot + 2), dst = (unsigned)__cvta_generic_to_shared(smem);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((unsigned)img_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(gimg), "r"((unsigned)img_bytes), "r"(mb) : "memory");
+    }
     unsigned done = 0;
     while (!done) {
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");

@@ -720,3 +720,49 @@ def test_per_env_body_shapes_match_oracle(backend, tmp_path):
     bad = copy.deepcopy(models[1]); bad.dof_limited = np.asarray(bad.dof_limited).copy(); bad.dof_limited[10] = 1 - bad.dof_limited[10]
     with pytest.raises(Exception):
         backend.batch(cfg_t[0], 4, models=[models[0], bad], env_model=[0, 1, 0, 1])
+
+
+def test_free_joint_armature_matches_oracle(backend):
+    """The root's six dofs are solved as one 6 x 6 system (A + S diag(armature) S^T) a = -p across the lanes of the env.  The shipped
+    models have no armature on the free joint (MuJoCo's <freejoint>), so this branch is pinned with a model that has: anisotropic
+    armature on the six root dofs (a <joint type="free" armature=...> with per-dof values), one mj_step from contact states and
+    stable-PD env steps against the oracle (which adds the armature to the diagonal of M)."""
+    import copy
+    from smplsim_b200.abi import env_cfg_from, model_from_cfg
+    cfg, om0 = make_models(control_mode="uhc_pd")
+    arm6 = np.array([0.8, 1.5, 0.4, 0.06, 0.02, 0.11])
+    def with_arm(c, seed=0):
+        m = copy.deepcopy(model_from_cfg(c))
+        m.dof_armature = np.asarray(m.dof_armature, dtype=np.float64).copy()
+        m.dof_armature[:6] = arm6
+        return m, orc.OracleModel(m, env_cfg_from(c, m, seed=seed))
+    cfg_t, _ = make_models(control_mode="torque")
+    m_t, om_t = with_arm(cfg_t)
+    n = 24
+    q, v, w = rollout_states(om0, n, seed=13)
+    rng = np.random.default_rng(5)
+    ctrl = rng.uniform(-80, 80, (n, m_t.nu))
+    env = backend.batch(cfg_t, n, models=[m_t], env_model=np.zeros(n, dtype=np.int32))
+    env.set_state(backend.t(q), backend.t(v)); env.qacc_warm.copy_(backend.t(w))
+    env.mj_step(backend.t(ctrl), 1)
+    gq, gv = env.qpos.cpu().numpy(), env.qvel.cpu().numpy()
+    differs = 0
+    om_plain = make_models(control_mode="torque")[1]          # the same model without the root armature
+    for i in range(n):
+        e = _oracle_one_step(om_t, q[i], v[i], w[i], ctrl[i])
+        e0 = _oracle_one_step(om_plain, q[i], v[i], w[i], ctrl[i]) if i < 4 else None
+        assert relerr(gv[i], e.qvel) < 2e-4 and relerr(gq[i], e.qpos) < TOL, (i, relerr(gv[i], e.qvel), relerr(gq[i], e.qpos))
+        if e0 is not None and relerr(e0.qvel, e.qvel) > 1e-3:
+            differs += 1
+    assert differs >= 2          # the armature matters: the same states step differently without it
+    m_p, om_p = with_arm(cfg, seed=3)
+    env2 = backend.batch(cfg, 8, seed=3, models=[m_p], env_model=np.zeros(8, dtype=np.int32))
+    obs0 = env2.reset().cpu().numpy().copy()
+    oes = [orc.OracleEnv(om_p, env_id=i) for i in range(8)]
+    for i, e in enumerate(oes):
+        assert np.abs(obs0[i] - e.reset()).max() < 1e-5
+    for t in range(2):
+        act = np.clip(rng.normal(size=(8, m_p.nu)) * 0.1, -1, 1)
+        obs = env2.step(backend.t(act))[0].cpu().numpy()
+        for i, e in enumerate(oes):
+            assert np.abs(obs[i] - e.step(act[i])[0]).max() < 1e-3 * (t + 1), (t, i)
