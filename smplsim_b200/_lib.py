@@ -11,7 +11,11 @@ SO_PATH = os.environ.get("SMPLSIM_SO") or os.path.join(_HERE, "libsmplsim_b200.s
 _CSRC = os.path.join(_HERE, "csrc")
 _LIB = None
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
+# -ftz / -prec-div / -prec-sqrt: denormals flushed, division and square root at 2 ulp (MUFU + one Newton step instead of the IEEE
+# sequences with their slow paths and denormal guards).  FMA contraction and everything else stay as in the default mode; the parity
+# tolerances (1e-4 against the fp64 oracle) are met with a wide margin, and the step kernel is 6 % faster.
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ftz=true", "-prec-div=false", "-prec-sqrt=false",
+              "-shared", "-Xcompiler", "-fPIC"]
 
 
 def sources():
