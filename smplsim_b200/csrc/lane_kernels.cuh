@@ -53,7 +53,7 @@ struct LCfg {
                        lim = con + CONW * NCS, pfl = lim + LIMW * NLS, PFLW = r4((NS + 3) / 4), misc = pfl + PFLW, tsk = misc + 8,
                        rec = tsk + 12, total_ = rec + (RECT ? 0 : RECW * NB);
   static constexpr int total = total_ | 4;   // env stride: a multiple of 4 words (float4 rows) but not of 8 (bank spread)
-  // staging of the final kinematics / observation row: aliases the mailboxes, root factors and contact list (dead by then).  When
+  // staging of the final kinematics / observation row: aliases the mailboxes, the root's 6 x 6 system and the contact list (dead by then).  When
   // the observation row does not fit beside the xquat rows (SMPL-X) it is written straight to global memory instead.
   static constexpr int OBSW = 4 * ((NB * 18 + 16 + 3) / 4);
   static constexpr bool OBS_STAGED = OBSW + 4 * NB <= lim - mbi;
@@ -573,7 +573,7 @@ __device__ __forceinline__ int l_narrow(const LHdr& H, const LGeom& G, int g, co
 }
 
 // root body of the outward sweep (free joint; lane 0 of the group, step 0; every lane makes the call): stable-PD
-// acceleration of the six root dofs from the stored factors, pose / velocity / bias acceleration of the state in qpos, qvel,
+// acceleration of the root (solved at the end of the last inward sweep), pose / velocity / bias acceleration of the state in qpos, qvel,
 // rigid inertia, bias force, contacts of the root's geom.  Children read the pose from the root's out-mailbox.
 struct LRootOut { int ncon, npresent; unsigned long long gbits; };
 template <class C>
@@ -1015,9 +1015,10 @@ __device__ __noinline__ int l_self_collide(const float* ms, float* sm, const LLa
   return nself;
 }
 
-// root body of the inward sweep (every lane makes the call; lane 0 of the group works): children arrive through the
-// in-mailboxes; (semi-implicit Euler of the free joint, then) elimination of its six dofs; the factors K (6 x 6), c (6) stay in
-// shared memory.  Returns "the root has constraint rows in its subtree".
+// root body of the inward sweep (every lane makes the call): children arrive through the in-mailboxes; lane 0 of the group assembles the
+// root's articulated inertia and bias force (after the semi-implicit Euler of the free joint in S4), the lanes of the group solve the
+// 6 x 6 system of its six dofs; the root's spatial acceleration stays in shared memory (LRT_A) for the outward sweeps.  Returns "the root
+// has constraint rows in its subtree" (lane 0).
 template <class C, bool SPD>
 __device__ __noinline__ bool l_root_in(const float* ms, float* sm, const LLane& w, bool need, int flags) {
   const LHdr& H = l_hdr<C>(ms);
